@@ -1,0 +1,53 @@
+/*
+ * radeonrays_cuda.h -- CUDA interop for the rr* API (the analogue of the reference's
+ * src/core/include/radeonrays_vlk.h:38-96 and radeonrays_dx.h:41-66).
+ *
+ * Signatures use only plain C types: a CUDA stream is passed as void* (cudaStream_t), device
+ * memory as void* (a CUDA device address).  Calling any of these on a context that was not
+ * created for RR_API_CUDA returns RR_ERROR_UNSUPPORTED_INTEROP (reference radeonrays.cpp:615-619).
+ */
+#ifndef RADEONRAYS_CUDA_H
+#define RADEONRAYS_CUDA_H
+
+#include "radeonrays.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Create a context on an existing device / stream (replaces rrCreateContextVk, radeonrays_vlk.h:38-43).
+ * cuda_stream may be NULL: the library then owns a non-blocking stream on `device_ordinal`. */
+RR_API RRError rrCreateContextCuda(uint32_t api_version, int device_ordinal, void* cuda_stream, RRContext* context);
+
+/* Wrap client-owned device memory (replaces rrGetDevicePtrFromVkBuffer, radeonrays_vlk.h:53-56).
+ * The client keeps ownership of the allocation; rrReleaseDevicePtr frees only the wrapper. */
+RR_API RRError rrGetDevicePtrFromCudaPtr(RRContext context, void* device_memory, size_t offset, RRDevicePtr* device_ptr);
+
+/* Wrap a client-owned cudaStream_t as a command stream (replaces rrGetCommandStreamFromVkCommandBuffer,
+ * radeonrays_vlk.h:64-66).  Release with rrReleaseExternalCommandStream. */
+RR_API RRError rrGetCommandStreamFromCudaStream(RRContext context, void* cuda_stream, RRCommandStream* command_stream);
+
+/* Library-owned device buffers + host mapping (same names and meaning as radeonrays_vlk.h:74-96;
+ * used by the reference's internal_resources_test.h:51-236).  Map returns a pinned host shadow that
+ * holds the current device contents; Unmap writes the shadow back to the device and frees it. */
+RR_API RRError rrAllocateDeviceBuffer(RRContext context, size_t size, RRDevicePtr* device_ptr);
+RR_API RRError rrMapDevicePtr(RRContext context, RRDevicePtr device_ptr, void** mapping_ptr);
+RR_API RRError rrUnmapDevicePtr(RRContext context, RRDevicePtr device_ptr, void** mapping_ptr);
+
+/* ---- extensions without a reference counterpart (documented in DESIGN.md) -------------------- */
+
+/* Raw device address behind an RRDevicePtr (base + offset). */
+RR_API RRError rrGetCudaPtrFromDevicePtr(RRContext context, RRDevicePtr device_ptr, void** device_memory);
+
+/* Closest-hit tie rule.  0 (default): equal-t hits resolve to the lowest (inst_id, prim_id), the rule
+ * BASELINE.json's north_star states.  1: keep the first hit found in traversal order, which is what
+ * the reference shader does (vlk/kernels/isect.comp:179, `t < closest_t`). */
+RR_API RRError rrCudaSetClosestHitTieRule(RRContext context, int keep_first_found);
+
+/* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches evidence). */
+RR_API RRError rrCudaGetLaunchCount(RRContext context, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADEONRAYS_CUDA_H */
