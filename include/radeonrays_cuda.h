@@ -39,10 +39,19 @@ RR_API RRError rrUnmapDevicePtr(RRContext context, RRDevicePtr device_ptr, void*
 /* Raw device address behind an RRDevicePtr (base + offset). */
 RR_API RRError rrGetCudaPtrFromDevicePtr(RRContext context, RRDevicePtr device_ptr, void** device_memory);
 
-/* Closest-hit tie rule.  0 (default): equal-t hits resolve to the lowest (inst_id, prim_id), the rule
- * BASELINE.json's north_star states.  1: keep the first hit found in traversal order, which is what
- * the reference shader does (vlk/kernels/isect.comp:179, `t < closest_t`). */
-RR_API RRError rrCudaSetClosestHitTieRule(RRContext context, int keep_first_found);
+/* Backend options.
+ * RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND: 0 (default) = equal-t closest hits resolve to the lowest
+ *   (inst_id, prim_id), the rule BASELINE.json's north_star states; 1 = keep the first hit found in traversal
+ *   order, which is what the reference shader does (vlk/kernels/isect.comp:179, `t < closest_t`).
+ * RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK: 0 (default) = instance boxes use all 8 corners of the BLAS box;
+ *   1 = reproduce the reference's corner set (vlk/kernels/common.h:282-289: pmax twice, (max,min,min) missing),
+ *   which can under-estimate the box of a rotated instance. */
+typedef enum
+{
+    RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND   = 1,
+    RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK = 2
+} RRCudaOption;
+RR_API RRError rrCudaSetOption(RRContext context, RRCudaOption option, int value);
 
 /* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches evidence). */
 RR_API RRError rrCudaGetLaunchCount(RRContext context, uint64_t* launches);

@@ -30,8 +30,27 @@ static inline v3    v3_make(float x, float y, float z) { v3 r = {x, y, z}; retur
 static inline v3    v3_ld(const float* p) { return v3_make(p[0], p[1], p[2]); }
 static inline void  v3_st(float* p, v3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
 static inline v3    v3_sub(v3 a, v3 b) { return v3_make(a.x - b.x, a.y - b.y, a.z - b.z); }
-static inline v3    v3_min(v3 a, v3 b) { return v3_make(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
-static inline v3    v3_max(v3 a, v3 b) { return v3_make(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+/* min/max with the zero ordering of IEEE 754-2019 minimum/maximum and of the GPU's FMNMX (-0.0 < +0.0) and
+ * the NaN rule of C fminf/fmaxf (return the other operand).  GLSL leaves both cases undefined; fixing them
+ * makes box bits reproducible (the Cornell box has both -0.0 and +0.0 y coordinates). */
+static inline float rr_min(float a, float b)
+{
+    if (a != a) return b;
+    if (b != b) return a;
+    if (a < b) return a;
+    if (b < a) return b;
+    return signbit(a) ? a : b;
+}
+static inline float rr_max(float a, float b)
+{
+    if (a != a) return b;
+    if (b != b) return a;
+    if (a > b) return a;
+    if (b > a) return b;
+    return signbit(a) ? b : a;
+}
+static inline v3    v3_min(v3 a, v3 b) { return v3_make(rr_min(a.x, b.x), rr_min(a.y, b.y), rr_min(a.z, b.z)); }
+static inline v3    v3_max(v3 a, v3 b) { return v3_make(rr_max(a.x, b.x), rr_max(a.y, b.y), rr_max(a.z, b.z)); }
 static inline float v3_dot(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 /* GLSL spec: cross(x,y) = (x1*y2 - y1*x2, x2*y0 - y2*x0, x0*y1 - y0*x1) */
 static inline v3 v3_cross(v3 a, v3 b)
@@ -99,9 +118,9 @@ static inline uint32_t expand_bits(uint32_t r)
 /* common.h:261-268.  clamp(x,lo,hi)=min(max(x,lo),hi); NaN -> 0 (fmaxf semantics). */
 static inline uint32_t morton_code(v3 p)
 {
-    float x = fminf(fmaxf(p.x * 1024.0f, 0.0f), 1023.0f);
-    float y = fminf(fmaxf(p.y * 1024.0f, 0.0f), 1023.0f);
-    float z = fminf(fmaxf(p.z * 1024.0f, 0.0f), 1023.0f);
+    float x = rr_min(rr_max(p.x * 1024.0f, 0.0f), 1023.0f);
+    float y = rr_min(rr_max(p.y * 1024.0f, 0.0f), 1023.0f);
+    float z = rr_min(rr_max(p.z * 1024.0f, 0.0f), 1023.0f);
     return (expand_bits((uint32_t)x) << 2) | (expand_bits((uint32_t)y) << 1) | expand_bits((uint32_t)z);
 }
 static inline uint32_t morton_of_box(v3 bmin, v3 bmax, v3 smin, v3 smax)
@@ -791,10 +810,10 @@ static inline void slab(const float* pmin, const float* pmax, v3 inv, v3 oxinv, 
 {
     float fx = fmaf(pmax[0], inv.x, oxinv.x), fy = fmaf(pmax[1], inv.y, oxinv.y), fz = fmaf(pmax[2], inv.z, oxinv.z);
     float nx = fmaf(pmin[0], inv.x, oxinv.x), ny = fmaf(pmin[1], inv.y, oxinv.y), nz = fmaf(pmin[2], inv.z, oxinv.z);
-    float ax = fmaxf(fx, nx), ay = fmaxf(fy, ny), az = fmaxf(fz, nz);
-    float ix = fminf(fx, nx), iy = fminf(fy, ny), iz = fminf(fz, nz);
-    *t1 = fminf(fminf(az, fminf(ax, ay)), t_max); /* mymin3(a,b,c)=min(c,min(a,b)) */
-    *t0 = fmaxf(fmaxf(iz, fmaxf(ix, iy)), t_min);
+    float ax = rr_max(fx, nx), ay = rr_max(fy, ny), az = rr_max(fz, nz);
+    float ix = rr_min(fx, nx), iy = rr_min(fy, ny), iz = rr_min(fz, nz);
+    *t1 = rr_min(rr_min(az, rr_min(ax, ay)), t_max); /* mymin3(a,b,c)=min(c,min(a,b)) */
+    *t0 = rr_max(rr_max(iz, rr_max(ix, iy)), t_min);
 }
 /* fast_intersect_triangle common.h:103-137; returns 1 and *t on acceptance by the shader's bounds test */
 static inline int tri_test(v3 o, v3 d, float min_t, const float* pv0, const float* pv1, const float* pv2, float t_max,

@@ -1,0 +1,623 @@
+// rr_api.cpp -- the rr* C ABI over the CUDA backend.
+//
+// Mirrors the reference's API shim (src/core/src/radeonrays.cpp): the same null checks returning
+// RR_ERROR_INVALID_PARAMETER, every C++ exception mapped to RR_ERROR_INTERNAL (CUDA out-of-memory to
+// RR_ERROR_OUT_OF_DEVICE_MEMORY), wrong-backend interop calls to RR_ERROR_UNSUPPORTED_INTEROP, and the
+// record-then-submit execution model: rrCmd* only append closures to the command stream, nothing runs on
+// the GPU until rrSumbitCommandStream (radeonrays.cpp:504-529, vlk/device.cpp:221-240).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <new>
+
+#include "radeonrays_cuda.h"
+#include "radeonrays_cuda_debug.h"
+#include "rr_internal.h"
+
+namespace rr
+{
+// ---- logging (reference: utils/logger.h:33-79 over spdlog; rrSetLogLevel / rrSetLogFile) ---------------
+struct Logger
+{
+    std::mutex mu;
+    int        level = RR_LOG_LEVEL_WARN;
+    FILE*      file  = nullptr;
+    static Logger& get()
+    {
+        static Logger L;
+        static bool   init = false;
+        if (!init)
+        {
+            init = true;
+            if (const char* e = std::getenv("RR_LOG_LEVEL")) L.level = std::atoi(e);
+        }
+        return L;
+    }
+    void log(int lvl, const char* fmt, ...)
+    {
+        if (lvl < level) return;
+        static const char* names[] = {"", "debug", "info", "warn", "error"};
+        std::lock_guard<std::mutex> g(mu);
+        FILE* out = file ? file : stderr;
+        std::fprintf(out, "[rr-cuda][%s] ", names[lvl]);
+        va_list ap;
+        va_start(ap, fmt);
+        std::vfprintf(out, fmt, ap);
+        va_end(ap);
+        std::fputc('\n', out);
+        if (file) std::fflush(file);
+    }
+};
+#define RR_INFO(...) ::rr::Logger::get().log(RR_LOG_LEVEL_INFO, __VA_ARGS__)
+#define RR_DEBUG(...) ::rr::Logger::get().log(RR_LOG_LEVEL_DEBUG, __VA_ARGS__)
+#define RR_ERR(...) ::rr::Logger::get().log(RR_LOG_LEVEL_ERROR, __VA_ARGS__)
+
+// ---- runtime objects (reference: base/*.h interfaces, vlk/{device,command_stream,event,device_ptr}.h) ---
+struct DevicePtr
+{
+    char*  base        = nullptr;
+    size_t offset      = 0;
+    size_t size        = 0;        // 0 = unknown (client memory)
+    bool   owned       = false;    // allocated by rrAllocateDeviceBuffer
+    void*  host_shadow = nullptr;  // pinned mapping while mapped
+    char*  ptr() const { return base + offset; }
+    size_t bytes_available() const { return size ? size - offset : (size_t)-1; }
+    ~DevicePtr()
+    {
+        if (host_shadow) cudaFreeHost(host_shadow);
+        if (owned && base) cudaFree(base);
+    }
+};
+
+struct Event
+{
+    cudaEvent_t ev = nullptr;
+    ~Event() { if (ev) cudaEventDestroy(ev); }
+};
+
+struct CommandStream
+{
+    cudaStream_t stream   = nullptr;
+    bool         external = false;
+    std::vector<std::function<void(cudaStream_t)>> commands;
+};
+
+struct Context
+{
+    RRApi        api        = RR_API_CUDA;
+    DeviceInfo   dev;
+    cudaStream_t stream     = nullptr;
+    bool         own_stream = false;
+    uint64_t     launches   = 0;
+    bool         first_found_tie_rule   = false;
+    bool         reference_corner_quirk = false;
+    std::map<const void*, uint32_t> scenes;  // scene buffer address -> instance count (vlk/intersector.cpp:86,263)
+    ~Context()
+    {
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+static RRError map_exception()
+{
+    try { throw; }
+    catch (const CudaError& e)
+    {
+        RR_ERR("%s", e.what());
+        return e.code == cudaErrorMemoryAllocation ? RR_ERROR_OUT_OF_DEVICE_MEMORY : RR_ERROR_INTERNAL;
+    }
+    catch (const std::bad_alloc&) { return RR_ERROR_OUT_OF_HOST_MEMORY; }
+    catch (const std::exception& e) { RR_ERR("%s", e.what()); return RR_ERROR_INTERNAL; }
+    catch (...) { return RR_ERROR_INTERNAL; }
+}
+
+static RRError create_context(int device, void* stream, RRContext* out)
+{
+    int count = 0;
+    RR_CUDA_CHECK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) throw std::runtime_error("no such CUDA device");
+    RR_CUDA_CHECK(cudaSetDevice(device));
+    std::unique_ptr<Context> ctx(new Context);
+    ctx->dev.device = device;
+    cudaDeviceProp prop;
+    RR_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    ctx->dev.sm_count = prop.multiProcessorCount;
+    ctx->dev.l2_bytes = (size_t)prop.l2CacheSize;
+    ctx->dev.launches = &ctx->launches;
+    if (stream) ctx->stream = static_cast<cudaStream_t>(stream);
+    else
+    {
+        RR_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    RR_INFO("CUDA context on device %d (%s, %d SMs)", device, prop.name, prop.multiProcessorCount);
+    *out = reinterpret_cast<RRContext>(ctx.release());
+    return RR_SUCCESS;
+}
+
+static inline Context*       C(RRContext c) { return reinterpret_cast<Context*>(c); }
+static inline DevicePtr*     D(RRDevicePtr p) { return reinterpret_cast<DevicePtr*>(p); }
+static inline CommandStream* S(RRCommandStream s) { return reinterpret_cast<CommandStream*>(s); }
+static inline Event*         E(RREvent e) { return reinterpret_cast<Event*>(e); }
+
+static bool wants_restructure(const RRBuildOptions* o)
+{   // vlk/intersector.cpp:116-119,170
+    return o && (o->build_flags & RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD) == 0;
+}
+
+// GetTriangleMeshBuildInfo, radeonrays.cpp:59-74 (one mesh per geometry, vlk/intersector.cpp:110,146)
+static RRError mesh_from_input(const RRGeometryBuildInput* in, MeshDesc& m)
+{
+    if (in->primitive_type != RR_PRIMITIVE_TYPE_TRIANGLE_MESH) return RR_ERROR_NOT_IMPLEMENTED;
+    if (in->primitive_count == 0 || !in->triangle_mesh_primitives) return RR_ERROR_INVALID_PARAMETER;
+    if (in->primitive_count != 1) return RR_ERROR_NOT_IMPLEMENTED;
+    const RRTriangleMeshPrimitive& p = in->triangle_mesh_primitives[0];
+    if (p.index_type != RR_INDEX_TYPE_UINT32) return RR_ERROR_NOT_IMPLEMENTED;
+    if (p.triangle_count == 0 || (p.vertex_stride & 3u) || p.vertex_stride < 12) return RR_ERROR_INVALID_PARAMETER;
+    m.vertices       = p.vertices ? reinterpret_cast<const float*>(D(p.vertices)->ptr()) : nullptr;
+    m.vertex_count   = p.vertex_count;
+    m.stride_floats  = p.vertex_stride >> 2;
+    m.indices        = p.triangle_indices ? reinterpret_cast<const uint32_t*>(D(p.triangle_indices)->ptr()) : nullptr;
+    m.triangle_count = p.triangle_count;
+    return RR_SUCCESS;
+}
+}  // namespace rr
+
+using namespace rr;
+
+extern "C" {
+
+RRError rrCreateContext(uint32_t api_version, RRApi api, RRContext* context)
+{
+    RR_INFO("rrCreateContext(%u)", api_version);
+    if (!context) return RR_ERROR_INVALID_PARAMETER;
+    if (api != RR_API_CUDA) return RR_ERROR_UNSUPPORTED_API;
+    try { return create_context(0, nullptr, context); }
+    catch (...) { return map_exception(); }
+}
+
+RRError rrCreateContextCuda(uint32_t api_version, int device_ordinal, void* cuda_stream, RRContext* context)
+{
+    RR_INFO("rrCreateContextCuda(%u, device %d)", api_version, device_ordinal);
+    if (!context) return RR_ERROR_INVALID_PARAMETER;
+    try { return create_context(device_ordinal, cuda_stream, context); }
+    catch (...) { return map_exception(); }
+}
+
+RRError rrDestroyContext(RRContext context)
+{
+    RR_INFO("rrDestroyContext");
+    if (!context) return RR_ERROR_INVALID_PARAMETER;
+    delete C(context);
+    return RR_SUCCESS;
+}
+
+RRError rrSetLogLevel(RRLogLevel log_level)
+{
+    if (log_level < RR_LOG_LEVEL_DEBUG || log_level > RR_LOG_LEVEL_OFF) return RR_ERROR_INVALID_PARAMETER;
+    Logger::get().level = log_level;
+    return RR_SUCCESS;
+}
+
+RRError rrSetLogFile(char const* filename)
+{
+    Logger& L = Logger::get();
+    std::lock_guard<std::mutex> g(L.mu);
+    if (L.file) { std::fclose(L.file); L.file = nullptr; }
+    if (filename)
+    {
+        L.file = std::fopen(filename, "w");
+        if (!L.file) return RR_ERROR_INTERNAL;
+    }
+    return RR_SUCCESS;
+}
+
+RRError rrGetGeometryBuildMemoryRequirements(RRContext context, const RRGeometryBuildInput* build_input,
+                                             const RRBuildOptions* build_options, RRMemoryRequirements* memory_requirements)
+{
+    RR_INFO("rrGetGeometryBuildMemoryRequirements");
+    if (!context || !build_input || !memory_requirements) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        MeshDesc m{};
+        if (RRError e = mesh_from_input(build_input, m)) return e;
+        const BlasLayout L = blas_layout(m.triangle_count, wants_restructure(build_options));
+        memory_requirements->result_buffer_size           = L.result_total;
+        memory_requirements->temporary_build_buffer_size  = L.scratch_total;
+        memory_requirements->temporary_update_buffer_size = 0;  // refit needs no scratch (vlk backend also reports 0)
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrCmdBuildGeometry(RRContext context, RRBuildOperation build_operation, const RRGeometryBuildInput* build_input,
+                           const RRBuildOptions* build_options, RRDevicePtr temporary_buffer, RRDevicePtr geometry_buffer,
+                           RRCommandStream command_stream)
+{
+    RR_INFO("rrCmdBuildGeometry");
+    if (!context || !command_stream || !build_input) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        Context* ctx = C(context);
+        MeshDesc m{};
+        if (RRError e = mesh_from_input(build_input, m)) return e;
+        if (!m.vertices || !m.indices || !geometry_buffer) return RR_ERROR_INVALID_PARAMETER;
+        Node*            nodes = reinterpret_cast<Node*>(D(geometry_buffer)->ptr());
+        const DeviceInfo dev   = ctx->dev;
+        if (build_operation == RR_BUILD_OPERATION_BUILD)
+        {
+            if (!temporary_buffer) return RR_ERROR_INVALID_PARAMETER;
+            const bool       restructure = wants_restructure(build_options);
+            const BlasLayout L           = blas_layout(m.triangle_count, restructure);
+            if (D(temporary_buffer)->bytes_available() < L.scratch_total || D(geometry_buffer)->bytes_available() < L.result_total)
+                throw std::runtime_error("geometry build: buffer smaller than rrGetGeometryBuildMemoryRequirements reported");
+            void* scratch = D(temporary_buffer)->ptr();
+            ctx->scenes.erase(nodes);
+            S(command_stream)->commands.push_back([=](cudaStream_t s) { build_blas(dev, s, m, L, scratch, nodes, restructure); });
+        }
+        else
+        {   // UPDATE: temporary buffer ignored like the reference (vlk/intersector.cpp:176-204)
+            S(command_stream)->commands.push_back([=](cudaStream_t s) { update_blas(dev, s, m, nodes); });
+        }
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrGetSceneBuildMemoryRequirements(RRContext context, const RRSceneBuildInput* build_input, const RRBuildOptions*,
+                                          RRMemoryRequirements* memory_requirements)
+{
+    RR_INFO("rrGetSceneBuildMemoryRequirements");
+    if (!context || !build_input || !memory_requirements) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        const SceneLayout L = scene_layout(build_input->instance_count);
+        memory_requirements->result_buffer_size           = L.result_total;
+        memory_requirements->temporary_build_buffer_size  = L.scratch_total;
+        memory_requirements->temporary_update_buffer_size = 0;
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrCmdBuildScene(RRContext context, const RRSceneBuildInput* build_input, const RRBuildOptions*, RRDevicePtr temporary_buffer,
+                        RRDevicePtr scene_buffer, RRCommandStream command_stream)
+{
+    RR_INFO("rrCmdBuildScene");
+    if (!context || !command_stream || !build_input) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        Context* ctx = C(context);
+        const uint32_t n = build_input->instance_count;
+        if (n == 0 || !build_input->instances || !temporary_buffer || !scene_buffer) return RR_ERROR_INVALID_PARAMETER;
+        // Host data is consumed at record time (vlk/intersector.cpp:222-247).
+        auto descs = std::make_shared<std::vector<InstanceDesc>>(n);
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            if (!build_input->instances[i].geometry) return RR_ERROR_INVALID_PARAMETER;
+            InstanceDesc& d = (*descs)[i];
+            std::memcpy(d.m, &build_input->instances[i].transform[0][0], 12 * sizeof(float));
+            d.blas  = reinterpret_cast<const Node*>(D(build_input->instances[i].geometry)->ptr());
+            d.index = i;
+            d.pad   = 0;
+        }
+        const SceneLayout L = scene_layout(n);
+        if (D(temporary_buffer)->bytes_available() < L.scratch_total || D(scene_buffer)->bytes_available() < L.result_total)
+            throw std::runtime_error("scene build: buffer smaller than rrGetSceneBuildMemoryRequirements reported");
+        void*            scratch = D(temporary_buffer)->ptr();
+        void*            scene   = D(scene_buffer)->ptr();
+        const DeviceInfo dev     = ctx->dev;
+        const bool       quirk   = ctx->reference_corner_quirk;
+        S(command_stream)->commands.push_back([=](cudaStream_t s) {
+            build_scene(dev, s, descs->data(), L, scratch, scene, quirk);
+            // the pageable host vector is staged synchronously by cudaMemcpyAsync; `descs` stays alive with the closure
+        });
+        ctx->scenes[scene] = n;
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrGetTraceMemoryRequirements(RRContext context, uint32_t ray_count, size_t* scratch_size)
+{
+    RR_INFO("rrGetTraceMemoryRequirements");
+    if (!context || !scratch_size || !ray_count) return RR_ERROR_INVALID_PARAMETER;
+    *scratch_size = trace_scratch_size(C(context)->dev, ray_count);
+    return RR_SUCCESS;
+}
+
+RRError rrCmdIntersect(RRContext context, RRDevicePtr scene_buffer, RRIntersectQuery query, RRDevicePtr rays, uint32_t ray_count,
+                       RRDevicePtr indirect_ray_count, RRIntersectQueryOutput query_output, RRDevicePtr hits, RRDevicePtr scratch,
+                       RRCommandStream command_stream)
+{
+    RR_INFO("rrCmdIntersect");
+    if (!context || !scene_buffer || !rays || !hits || !scratch || !command_stream) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        Context*  ctx = C(context);
+        TraceArgs a{};
+        char*     scene = D(scene_buffer)->ptr();
+        auto      it    = ctx->scenes.find(scene);
+        if (it != ctx->scenes.end())
+        {   // two level: the buffer was produced by rrCmdBuildScene (vlk/intersector.cpp:289-324)
+            const SceneLayout L = scene_layout(it->second);
+            a.bvh       = reinterpret_cast<const Node*>(scene + L.nodes_off);
+            a.instances = reinterpret_cast<const InstanceRecord*>(scene + L.records_off);
+        }
+        else
+        {
+            a.bvh       = reinterpret_cast<const Node*>(scene);
+            a.instances = nullptr;
+        }
+        a.rays           = reinterpret_cast<const RRRay*>(D(rays)->ptr());
+        a.ray_count      = ray_count;
+        a.indirect_count = indirect_ray_count ? reinterpret_cast<const uint32_t*>(D(indirect_ray_count)->ptr()) : nullptr;
+        a.hits           = D(hits)->ptr();
+        a.scratch        = reinterpret_cast<uint32_t*>(D(scratch)->ptr());
+        a.scratch_bytes  = D(scratch)->bytes_available();
+        a.query          = query;
+        a.output         = query_output;
+        a.first_found_tie_rule = ctx->first_found_tie_rule;
+        if (ray_count && a.scratch_bytes < trace_scratch_size(ctx->dev, ray_count))
+            throw std::runtime_error("intersect: scratch smaller than rrGetTraceMemoryRequirements reported");
+        const DeviceInfo dev = ctx->dev;
+        S(command_stream)->commands.push_back([=](cudaStream_t s) { trace(dev, s, a); });
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrAllocateCommandStream(RRContext context, RRCommandStream* command_stream)
+{
+    RR_INFO("rrAllocateCommandStream");
+    if (!context || !command_stream) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        CommandStream* s = new CommandStream;
+        s->stream        = C(context)->stream;
+        *command_stream  = reinterpret_cast<RRCommandStream>(s);
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrReleaseCommandStream(RRContext context, RRCommandStream command_stream)
+{
+    RR_INFO("rrReleaseCommandStream");
+    if (!context || !command_stream) return RR_ERROR_INVALID_PARAMETER;
+    delete S(command_stream);
+    return RR_SUCCESS;
+}
+
+RRError rrReleaseExternalCommandStream(RRContext context, RRCommandStream command_stream)
+{
+    RR_INFO("rrReleaseExternalCommandStream");
+    if (!context || !command_stream) return RR_ERROR_INVALID_PARAMETER;
+    delete S(command_stream);
+    return RR_SUCCESS;
+}
+
+RRError rrSumbitCommandStream(RRContext context, RRCommandStream command_stream, RREvent wait_event, RREvent* out_event)
+{
+    RR_INFO("rrSumbitCommandStream");
+    if (!context || !command_stream || !out_event) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        Context*       ctx = C(context);
+        CommandStream* cs  = S(command_stream);
+        RR_CUDA_CHECK(cudaSetDevice(ctx->dev.device));
+        // GPU-side wait: satisfies both the Vulkan (CPU wait, vlk/device.cpp:229-232) and DX12 (queue wait) contracts.
+        if (wait_event) RR_CUDA_CHECK(cudaStreamWaitEvent(cs->stream, E(wait_event)->ev, 0));
+        for (auto& cmd : cs->commands) cmd(cs->stream);
+        std::unique_ptr<Event> ev(new Event);
+        RR_CUDA_CHECK(cudaEventCreateWithFlags(&ev->ev, cudaEventDisableTiming));
+        RR_CUDA_CHECK(cudaEventRecord(ev->ev, cs->stream));
+        *out_event = reinterpret_cast<RREvent>(ev.release());
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrReleaseEvent(RRContext context, RREvent event)
+{
+    RR_INFO("rrReleaseEvent");
+    if (!context || !event) return RR_ERROR_INVALID_PARAMETER;
+    delete E(event);
+    return RR_SUCCESS;
+}
+
+RRError rrWaitEvent(RRContext context, RREvent event)
+{
+    RR_INFO("rrWaitEvent");
+    if (!context || !event) return RR_ERROR_INVALID_PARAMETER;
+    try { RR_CUDA_CHECK(cudaEventSynchronize(E(event)->ev)); }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrReleaseDevicePtr(RRContext context, RRDevicePtr ptr)
+{
+    RR_INFO("rrReleaseDevicePtr");
+    if (!context || !ptr) return RR_ERROR_INVALID_PARAMETER;
+    delete D(ptr);
+    return RR_SUCCESS;
+}
+
+// ---- CUDA interop (radeonrays_cuda.h) ------------------------------------------------------------------
+RRError rrGetDevicePtrFromCudaPtr(RRContext context, void* device_memory, size_t offset, RRDevicePtr* device_ptr)
+{
+    if (!context || !device_memory || !device_ptr) return RR_ERROR_INVALID_PARAMETER;
+    if (C(context)->api != RR_API_CUDA) return RR_ERROR_UNSUPPORTED_INTEROP;
+    try
+    {
+        DevicePtr* p = new DevicePtr;
+        p->base      = static_cast<char*>(device_memory);
+        p->offset    = offset;
+        *device_ptr  = reinterpret_cast<RRDevicePtr>(p);
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrGetCommandStreamFromCudaStream(RRContext context, void* cuda_stream, RRCommandStream* command_stream)
+{
+    // NULL is the legacy default stream, a valid cudaStream_t, so only the out pointer is checked.
+    if (!context || !command_stream) return RR_ERROR_INVALID_PARAMETER;
+    if (C(context)->api != RR_API_CUDA) return RR_ERROR_UNSUPPORTED_INTEROP;
+    try
+    {
+        CommandStream* s = new CommandStream;
+        s->stream        = static_cast<cudaStream_t>(cuda_stream);
+        s->external      = true;
+        *command_stream  = reinterpret_cast<RRCommandStream>(s);
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrAllocateDeviceBuffer(RRContext context, size_t size, RRDevicePtr* device_ptr)
+{
+    if (!context || !size || !device_ptr) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        RR_CUDA_CHECK(cudaSetDevice(C(context)->dev.device));
+        std::unique_ptr<DevicePtr> p(new DevicePtr);
+        void* mem = nullptr;
+        RR_CUDA_CHECK(cudaMalloc(&mem, size));
+        p->base  = static_cast<char*>(mem);
+        p->size  = size;
+        p->owned = true;
+        *device_ptr = reinterpret_cast<RRDevicePtr>(p.release());
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrMapDevicePtr(RRContext context, RRDevicePtr device_ptr, void** mapping_ptr)
+{
+    if (!context || !device_ptr || !mapping_ptr) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        DevicePtr* p = D(device_ptr);
+        if (!p->size) throw std::runtime_error("rrMapDevicePtr: only buffers from rrAllocateDeviceBuffer can be mapped");
+        RR_CUDA_CHECK(cudaSetDevice(C(context)->dev.device));
+        if (!p->host_shadow) RR_CUDA_CHECK(cudaMallocHost(&p->host_shadow, p->size));
+        // Everything previously submitted must be visible in the mapping.
+        RR_CUDA_CHECK(cudaDeviceSynchronize());
+        RR_CUDA_CHECK(cudaMemcpy(p->host_shadow, p->base, p->size, cudaMemcpyDeviceToHost));
+        *mapping_ptr = static_cast<char*>(p->host_shadow) + p->offset;
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrUnmapDevicePtr(RRContext context, RRDevicePtr device_ptr, void** mapping_ptr)
+{
+    if (!context || !device_ptr || !mapping_ptr) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        DevicePtr* p = D(device_ptr);
+        if (!p->host_shadow) throw std::runtime_error("rrUnmapDevicePtr: buffer is not mapped");
+        RR_CUDA_CHECK(cudaSetDevice(C(context)->dev.device));
+        RR_CUDA_CHECK(cudaMemcpy(p->base, p->host_shadow, p->size, cudaMemcpyHostToDevice));
+        RR_CUDA_CHECK(cudaFreeHost(p->host_shadow));
+        p->host_shadow = nullptr;
+        *mapping_ptr   = nullptr;
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrGetCudaPtrFromDevicePtr(RRContext context, RRDevicePtr device_ptr, void** device_memory)
+{
+    if (!context || !device_ptr || !device_memory) return RR_ERROR_INVALID_PARAMETER;
+    *device_memory = D(device_ptr)->ptr();
+    return RR_SUCCESS;
+}
+
+RRError rrCudaSetOption(RRContext context, RRCudaOption option, int value)
+{
+    if (!context) return RR_ERROR_INVALID_PARAMETER;
+    switch (option)
+    {
+    case RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND: C(context)->first_found_tie_rule = value != 0; return RR_SUCCESS;
+    case RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK: C(context)->reference_corner_quirk = value != 0; return RR_SUCCESS;
+    default: return RR_ERROR_INVALID_PARAMETER;
+    }
+}
+
+RRError rrCudaGetLaunchCount(RRContext context, uint64_t* launches)
+{
+    if (!context || !launches) return RR_ERROR_INVALID_PARAMETER;
+    *launches = C(context)->launches;
+    return RR_SUCCESS;
+}
+
+// ---- debug / test hooks (radeonrays_cuda_debug.h) ------------------------------------------------------
+RRError rrCudaDebugGetBuildScratchLayout(RRContext context, uint32_t triangle_count, RRCudaBuildScratchLayout* layout)
+{
+    if (!context || !layout || !triangle_count) return RR_ERROR_INVALID_PARAMETER;
+    const BlasLayout L         = blas_layout(triangle_count, false);
+    layout->scene_aabb_offset   = L.aabb_off;
+    layout->morton_codes_offset = L.codes_off;
+    layout->sorted_codes_offset = L.sorted_codes_off;
+    layout->sorted_refs_offset  = L.sorted_refs_off;
+    return RR_SUCCESS;
+}
+
+RRError rrCudaDebugSortPairs(RRContext context, void* keys_in, void* values_in, void* keys_out, void* values_out, uint32_t count)
+{
+    if (!context || !keys_in || !keys_out || !values_out) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        Context* ctx = C(context);
+        RR_CUDA_CHECK(cudaSetDevice(ctx->dev.device));
+        if (count == 0) return RR_SUCCESS;
+        const SortLayout L = sort_layout(count);
+        void* scratch = nullptr;
+        RR_CUDA_CHECK(cudaMalloc(&scratch, L.total));
+        try
+        {
+            sort_reset(ctx->dev, ctx->stream, L, scratch);
+            sort_histogram(ctx->dev, ctx->stream, L, scratch, static_cast<const uint32_t*>(keys_in));
+            sort_pairs(ctx->dev, ctx->stream, L, scratch, static_cast<uint32_t*>(keys_in), static_cast<const uint32_t*>(values_in),
+                       static_cast<uint32_t*>(keys_out), static_cast<uint32_t*>(values_out));
+            RR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        }
+        catch (...) { cudaFree(scratch); throw; }
+        RR_CUDA_CHECK(cudaFree(scratch));
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrCudaDebugRestructure(RRContext context, RRDevicePtr geometry, uint32_t triangle_count, RRDevicePtr temporary_buffer)
+{
+    if (!context || !geometry || !temporary_buffer || !triangle_count) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        Context* ctx = C(context);
+        RR_CUDA_CHECK(cudaSetDevice(ctx->dev.device));
+        if (D(temporary_buffer)->bytes_available() < treelet_scratch_size(triangle_count))
+            throw std::runtime_error("restructure: temporary buffer too small");
+        restructure_blas(ctx->dev, ctx->stream, reinterpret_cast<Node*>(D(geometry)->ptr()), triangle_count, D(temporary_buffer)->ptr());
+        RR_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrCudaDebugGetSceneLayout(RRContext context, uint32_t instance_count, RRCudaSceneLayout* layout)
+{
+    if (!context || !layout || !instance_count) return RR_ERROR_INVALID_PARAMETER;
+    const SceneLayout L               = scene_layout(instance_count);
+    layout->nodes_offset              = L.nodes_off;
+    layout->records_offset            = L.records_off;
+    layout->forward_transforms_offset = L.fwd_off;
+    return RR_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,574 @@
+// rr_build.cu -- HLBVH build, refit and top-level build for sm_100a.
+//
+// What the reference does in 45+ dispatches (vlk/hlbvh_builder.cpp:159-351: init, scene AABB, Morton,
+// 8 x (histogram, scan, scatter), emit hierarchy, fit) runs here as:
+//   2 memset nodes -> k_scene_aabb -> k_morton (+ digit histograms) -> 4 onesweep passes -> k_emit_fit
+// k_emit_fit fuses hierarchy emission and bottom-up fitting: every node's 64 bytes are written once.
+// It produces the SAME tree, node numbering (Karras: internal i in [0,N-1), leaf j at N-1+j, root 0) and
+// boxes as lbvh_emit_hierarchy_mesh.comp:170-217 + lbvh_fit_aabb_mesh.comp:122-205 -- see the proof
+// sketch at k_emit_fit.  All arithmetic that feeds Morton codes is plain IEEE binary32 (the library is
+// compiled with --fmad=false).
+//
+// Algorithmic HBM bytes per triangle (u32 indices, 12-B vertices): aabb 48 + morton 48 + code write 4 +
+// sort 60 (identity values: no ref write/read in pass 0) + emit/fit: codes 8, refs 4, gather 48, nodes 128.
+#include <algorithm>
+
+#include "rr_internal.h"
+
+namespace rr
+{
+namespace
+{
+// ---- ordered-uint float encoding (reference: vlk/kernels/common.h:68-90) -----------------------------
+__device__ __forceinline__ uint32_t float_to_ordered(float f)
+{
+    uint32_t v = __float_as_uint(f);
+    return v ^ ((1u + ~(v >> 31)) | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t v) { return __uint_as_float(v ^ (((v >> 31) - 1u) | 0x80000000u)); }
+
+__device__ __forceinline__ float3 ld3(const float* p) { return make_float3(p[0], p[1], p[2]); }
+__device__ __forceinline__ float3 min3(float3 a, float3 b) { return make_float3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
+__device__ __forceinline__ float3 max3(float3 a, float3 b) { return make_float3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+__device__ __forceinline__ float3 xyz(float4 q) { return make_float3(q.x, q.y, q.z); }
+__device__ __forceinline__ float4 pack(float3 v, uint32_t w) { return make_float4(v.x, v.y, v.z, __uint_as_float(w)); }
+__device__ __forceinline__ uint32_t wbits(float4 q) { return __float_as_uint(q.w); }
+
+// common.h:251-268
+__device__ __forceinline__ uint32_t expand_bits(uint32_t r)
+{
+    r = (r * 0x00010001u) & 0xFF0000FFu;
+    r = (r * 0x00000101u) & 0x0F00F00Fu;
+    r = (r * 0x00000011u) & 0xC30C30C3u;
+    r = (r * 0x00000005u) & 0x49249249u;
+    return r;
+}
+// lbvh_calc_morton_codes_mesh.comp:114-125 + common.h:261-268.  NaN (zero extent) clamps to 0.
+__device__ __forceinline__ uint32_t morton_of_box(float3 bmin, float3 bmax, float3 smin, float3 smax)
+{
+    const float3 ext = make_float3(smax.x - smin.x, smax.y - smin.y, smax.z - smin.z);
+    const float3 c   = make_float3(0.5f * (bmin.x + bmax.x), 0.5f * (bmin.y + bmax.y), 0.5f * (bmin.z + bmax.z));
+    const float  px = (c.x - smin.x) / ext.x, py = (c.y - smin.y) / ext.y, pz = (c.z - smin.z) / ext.z;
+    const float  x = fminf(fmaxf(px * 1024.0f, 0.0f), 1023.0f);
+    const float  y = fminf(fmaxf(py * 1024.0f, 0.0f), 1023.0f);
+    const float  z = fminf(fmaxf(pz * 1024.0f, 0.0f), 1023.0f);
+    return (expand_bits((uint32_t)x) << 2) | (expand_bits((uint32_t)y) << 1) | expand_bits((uint32_t)z);
+}
+
+struct OrderedBox
+{
+    uint32_t lo[3], hi[3];
+    __device__ void init()
+    {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = 0xFFFFFFFFu; hi[a] = 0u; }
+    }
+    __device__ void grow(float3 p)
+    {
+        const uint32_t e[3] = {float_to_ordered(p.x), float_to_ordered(p.y), float_to_ordered(p.z)};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], e[a]); hi[a] = max(hi[a], e[a]); }
+    }
+};
+
+// CTA-wide reduction of an OrderedBox followed by 6 global atomics (lbvh_calc_mesh_aabb.comp:163-177).
+// g_aabb layout: [0..2] = min xyz, [4..6] = max xyz (ordered-uint encoding), like the reference's uint[8].
+__device__ __forceinline__ void reduce_box_to_global(OrderedBox b, uint32_t* g_aabb)
+{
+    __shared__ uint32_t s_red[6][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+        b.lo[a] = __reduce_min_sync(0xffffffffu, b.lo[a]);
+        b.hi[a] = __reduce_max_sync(0xffffffffu, b.hi[a]);
+    }
+    if (lane == 0)
+    {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { s_red[a][warp] = b.lo[a]; s_red[3 + a][warp] = b.hi[a]; }
+    }
+    __syncthreads();
+    if (warp == 0)
+    {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            uint32_t lo = lane < nwarps ? s_red[a][lane] : 0xFFFFFFFFu;
+            uint32_t hi = lane < nwarps ? s_red[3 + a][lane] : 0u;
+            lo          = __reduce_min_sync(0xffffffffu, lo);
+            hi          = __reduce_max_sync(0xffffffffu, hi);
+            if (lane == 0)
+            {
+                atomicMin(&g_aabb[a], lo);
+                atomicMax(&g_aabb[4 + a], hi);
+            }
+        }
+    }
+}
+
+// ---- K1: scene AABB over all referenced vertices (lbvh_calc_mesh_aabb.comp:121-178) -----------------
+__global__ void __launch_bounds__(256) k_scene_aabb(MeshDesc m, uint32_t* __restrict__ g_aabb)
+{
+    OrderedBox box;
+    box.init();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m.triangle_count; i += stride)
+    {
+        const uint32_t i0 = m.indices[3 * (size_t)i + 0], i1 = m.indices[3 * (size_t)i + 1], i2 = m.indices[3 * (size_t)i + 2];
+        box.grow(ld3(m.vertices + (size_t)i0 * m.stride_floats));
+        box.grow(ld3(m.vertices + (size_t)i1 * m.stride_floats));
+        box.grow(ld3(m.vertices + (size_t)i2 * m.stride_floats));
+    }
+    reduce_box_to_global(box, g_aabb);
+}
+
+__device__ __forceinline__ void load_scene_box(const uint32_t* g_aabb, float3& smin, float3& smax)
+{
+    smin = make_float3(ordered_to_float(g_aabb[0]), ordered_to_float(g_aabb[1]), ordered_to_float(g_aabb[2]));
+    smax = make_float3(ordered_to_float(g_aabb[4]), ordered_to_float(g_aabb[5]), ordered_to_float(g_aabb[6]));
+}
+
+// ---- K2: Morton codes + the 4x256 digit histograms the onesweep passes need --------------------------
+// kScene=false: triangles (lbvh_calc_morton_codes_mesh.comp:78-130); kScene=true: instance world boxes
+// (lbvh_calc_morton_codes_scene.comp:84-112).  ref[i]=i is implicit (identity values in sort pass 0).
+template <bool kScene>
+__global__ void __launch_bounds__(256)
+    k_morton(MeshDesc m, const float4* __restrict__ boxes, uint32_t count, const uint32_t* __restrict__ g_aabb,
+             uint32_t* __restrict__ codes, uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t s_hist[4 * 256];
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    float3 smin, smax;
+    load_scene_box(g_aabb, smin, smax);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    {
+        float3 bmin, bmax;
+        if (kScene)
+        {
+            bmin = xyz(boxes[2 * (size_t)i]);
+            bmax = xyz(boxes[2 * (size_t)i + 1]);
+        }
+        else
+        {
+            const uint32_t i0 = m.indices[3 * (size_t)i + 0], i1 = m.indices[3 * (size_t)i + 1], i2 = m.indices[3 * (size_t)i + 2];
+            const float3   v0 = ld3(m.vertices + (size_t)i0 * m.stride_floats);
+            const float3   v1 = ld3(m.vertices + (size_t)i1 * m.stride_floats);
+            const float3   v2 = ld3(m.vertices + (size_t)i2 * m.stride_floats);
+            bmin              = min3(min3(v0, v1), v2);
+            bmax              = max3(max3(v0, v1), v2);
+        }
+        const uint32_t code = morton_of_box(bmin, bmax, smin, smax);
+        codes[i]            = code;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p * 256 + ((code >> (8 * p)) & 255u)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+// ---- K4+K5 fused: hierarchy emission + bottom-up fit --------------------------------------------------
+// delta(a, a+1) of lbvh_emit_hierarchy_mesh.comp:85-103 up to a strictly monotone map (true clz instead
+// of the shader's 32-findMSB; only comparisons between deltas are ever used).
+__device__ __forceinline__ int delta_adjacent(const uint32_t* __restrict__ codes, uint32_t a)
+{
+    const uint32_t x = codes[a] ^ codes[a + 1];
+    return x ? __clz(x) : 32 + __clz(a ^ (a + 1));
+}
+
+struct EmitParams
+{
+    const uint32_t* codes;   // sorted
+    const uint32_t* refs;    // sorted primitive / instance ids
+    uint32_t        n;
+    uint32_t*       flags;   // [n-1], preset to 0xFFFFFFFF: rendezvous word per split position
+    Node*           nodes;
+    // mesh leaves
+    MeshDesc mesh;
+    // scene leaves
+    const float4*       boxes;    // [2n] world boxes per instance
+    const InstanceDesc* descs;    // [n]
+    InstanceRecord*     records;  // [n]
+    float4*             fwd;      // [3n] forward transforms (kept for layout parity with the reference's transforms[2i+1])
+};
+
+__device__ __forceinline__ void node_box(const float4 q0, const float4 q1, const float4 q2, const float4 q3, bool tri_leaf,
+                                         float3& lo, float3& hi)
+{
+    if (tri_leaf)
+    {   // calculate_aabb_for_triangle, common.h:241-248
+        lo = min3(min3(xyz(q0), xyz(q1)), xyz(q2));
+        hi = max3(max3(xyz(q0), xyz(q1)), xyz(q2));
+    }
+    else
+    {   // union of the two stored child boxes, lbvh_fit_aabb_mesh.comp:98-110
+        lo = min3(xyz(q0), xyz(q2));
+        hi = max3(xyz(q1), xyz(q3));
+    }
+}
+
+// Affine inverse with a fixed expression tree (the oracle evaluates the same one; GLSL inverse(mat4),
+// common.h:326-342, is implementation defined).
+__device__ __forceinline__ void affine_inverse(const float* m, float4& r0, float4& r1, float4& r2)
+{
+    const float a00 = m[0], a01 = m[1], a02 = m[2], tx = m[3];
+    const float a10 = m[4], a11 = m[5], a12 = m[6], ty = m[7];
+    const float a20 = m[8], a21 = m[9], a22 = m[10], tz = m[11];
+    const float c00 = a11 * a22 - a12 * a21, c01 = a02 * a21 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+    const float c10 = a12 * a20 - a10 * a22, c11 = a00 * a22 - a02 * a20, c12 = a02 * a10 - a00 * a12;
+    const float c20 = a10 * a21 - a11 * a20, c21 = a01 * a20 - a00 * a21, c22 = a00 * a11 - a01 * a10;
+    const float det = (a00 * c00 + a01 * c10) + a02 * c20;
+    const float inv = 1.0f / det;
+    const float r00 = c00 * inv, r01 = c01 * inv, r02 = c02 * inv;
+    const float r10 = c10 * inv, r11 = c11 * inv, r12 = c12 * inv;
+    const float r20 = c20 * inv, r21 = c21 * inv, r22 = c22 * inv;
+    r0 = make_float4(r00, r01, r02, -((r00 * tx + r01 * ty) + r02 * tz));
+    r1 = make_float4(r10, r11, r12, -((r10 * tx + r11 * ty) + r12 * tz));
+    r2 = make_float4(r20, r21, r22, -((r20 * tx + r21 * ty) + r22 * tz));
+}
+
+// One thread per leaf.  A thread owns a sorted-key range [l,r] (initially its leaf) and climbs:
+//   * [l,r] is the left child of its parent iff l==0 or (r!=n-1 and delta(r,r+1) > delta(l-1,l)) -- the
+//     parent merges with the neighbour sharing the longer prefix (ties are impossible for a valid radix
+//     tree node because the index-augmented keys are distinct and sorted).
+//   * both children meet at flags[split]; the first to arrive leaves its far bound there and retires, the
+//     second learns the sibling's bound, hence the parent's range [L,R], and emits the parent.
+//   * Karras numbering: a non-root internal node is stored at index R if it is a left child (it IS its
+//     parent's split position) and at L if it is a right child (split+1); the root is 0.  This is exactly
+//     the index FindSpan/FindSplit assign top-down, so child0/child1/parent match the reference bit for bit.
+// Boxes are pure min/max, so fitting in arrival order is bit-exact too.
+template <bool kScene>
+__global__ void __launch_bounds__(256) k_emit_fit(EmitParams p)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.n) return;
+    const uint32_t n = p.n, leaf0 = n - 1;
+    const uint32_t ref = p.refs[j];
+    float3 lo, hi;
+    uint32_t me = leaf0 + j;
+    if (kScene)
+    {   // lbvh_fit_aabb_scene.comp:113-130
+        const float4 bmin = p.boxes[2 * (size_t)ref], bmax = p.boxes[2 * (size_t)ref + 1];
+        lo = xyz(bmin);
+        hi = xyz(bmax);
+        const InstanceDesc d = p.descs[ref];
+        InstanceRecord rec;
+        affine_inverse(d.m, rec.inv0, rec.inv1, rec.inv2);
+        rec.blas = d.blas;
+        rec.pad  = 0;
+        p.records[ref]     = rec;
+        p.fwd[3 * (size_t)ref + 0] = make_float4(d.m[0], d.m[1], d.m[2], d.m[3]);
+        p.fwd[3 * (size_t)ref + 1] = make_float4(d.m[4], d.m[5], d.m[6], d.m[7]);
+        p.fwd[3 * (size_t)ref + 2] = make_float4(d.m[8], d.m[9], d.m[10], d.m[11]);
+        Node* nd = p.nodes + me;
+        nd->q0 = pack(lo, kInvalid);
+        nd->q1 = pack(hi, ref);
+        nd->q2 = pack(lo, kInvalid);
+        nd->q3 = pack(hi, 0u);
+    }
+    else
+    {   // lbvh_fit_aabb_mesh.comp:139-163
+        const uint32_t i0 = p.mesh.indices[3 * (size_t)ref + 0], i1 = p.mesh.indices[3 * (size_t)ref + 1],
+                       i2 = p.mesh.indices[3 * (size_t)ref + 2];
+        const float3 v0 = ld3(p.mesh.vertices + (size_t)i0 * p.mesh.stride_floats);
+        const float3 v1 = ld3(p.mesh.vertices + (size_t)i1 * p.mesh.stride_floats);
+        const float3 v2 = ld3(p.mesh.vertices + (size_t)i2 * p.mesh.stride_floats);
+        lo = min3(min3(v0, v1), v2);
+        hi = max3(max3(v0, v1), v2);
+        Node* nd = p.nodes + me;
+        nd->q0 = pack(v0, kInvalid);
+        nd->q1 = pack(v1, ref);
+        nd->q2 = pack(v2, kInvalid);
+        nd->q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    uint32_t l = j, r = j;
+    bool is_root = (n == 1);
+    bool is_left = false;
+    if (!is_root) is_left = (l == 0) || (r != n - 1 && delta_adjacent(p.codes, r) > delta_adjacent(p.codes, l - 1));
+    while (!is_root)
+    {
+        const uint32_t split = is_left ? r : l - 1;
+        __threadfence();  // publish my node before announcing arrival
+        const uint32_t other = atomicExch(&p.flags[split], is_left ? l : r);
+        if (other == kInvalid) return;  // first to arrive: the sibling's thread finishes the parent
+        __threadfence();
+        uint32_t sib, L, R;
+        if (is_left) { L = l; R = other; sib = (split + 1 == R) ? leaf0 + split + 1 : split + 1; }
+        else { L = other; R = r; sib = (L == split) ? leaf0 + split : split; }
+        const float4* sp = reinterpret_cast<const float4*>(p.nodes + sib);
+        const float4 s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2), s3 = __ldcg(sp + 3);
+        float3 slo, shi;
+        node_box(s0, s1, s2, s3, !kScene && sib >= leaf0, slo, shi);
+
+        is_root = (L == 0 && R == n - 1);
+        bool parent_is_left = false;
+        if (!is_root) parent_is_left = (L == 0) || (R != n - 1 && delta_adjacent(p.codes, R) > delta_adjacent(p.codes, L - 1));
+        const uint32_t parent = is_root ? 0u : (parent_is_left ? R : L);
+        Node* pn = p.nodes + parent;
+        if (is_left)
+        {
+            pn->q0 = pack(lo, me);
+            pn->q1 = pack(hi, sib);
+            pn->q2 = pack(slo, kInvalid);
+            pn->q3 = pack(shi, 0u);
+        }
+        else
+        {
+            pn->q0 = pack(slo, sib);
+            pn->q1 = pack(shi, me);
+            pn->q2 = pack(lo, kInvalid);
+            pn->q3 = pack(hi, 0u);
+        }
+        reinterpret_cast<uint32_t*>(p.nodes + me)[11]  = parent;  // q2.w = parent
+        reinterpret_cast<uint32_t*>(p.nodes + sib)[11] = parent;
+        lo = min3(lo, slo);
+        hi = max3(hi, shi);
+        l = L; r = R; me = parent; is_left = parent_is_left;
+    }
+    // root (also the N==1 leaf): parent = INVALID
+    reinterpret_cast<uint32_t*>(p.nodes + me)[11] = kInvalid;
+}
+
+// ---- K6: refit / update (lbvh_fit_aabb_mesh.comp with UPDATE_KERNEL, vlk/update_hlbvh.cpp:118-185) ----
+// Topology untouched.  The rendezvous counter is the node's own `update` word used as a parity bit
+// (atomicAdd; even = first arrival), so no reset pass and no scratch are needed -- the reference's
+// reset kernel covers only the first 1024 primitives.
+__global__ void __launch_bounds__(256) k_refit(MeshDesc m, Node* __restrict__ nodes, uint32_t n)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t leaf0 = n - 1;
+    uint32_t me = leaf0 + j;
+    float4* np = reinterpret_cast<float4*>(nodes + me);
+    const float4 q1 = np[1], q2 = np[2];
+    const uint32_t prim = wbits(q1);
+    uint32_t parent = wbits(q2);
+    const uint32_t i0 = m.indices[3 * (size_t)prim + 0], i1 = m.indices[3 * (size_t)prim + 1], i2 = m.indices[3 * (size_t)prim + 2];
+    const float3 v0 = ld3(m.vertices + (size_t)i0 * m.stride_floats);
+    const float3 v1 = ld3(m.vertices + (size_t)i1 * m.stride_floats);
+    const float3 v2 = ld3(m.vertices + (size_t)i2 * m.stride_floats);
+    np[0] = pack(v0, kInvalid);
+    np[1] = pack(v1, prim);
+    np[2] = pack(v2, parent);
+    float3 lo = min3(min3(v0, v1), v2), hi = max3(max3(v0, v1), v2);
+    while (parent != kInvalid)
+    {
+        __threadfence();
+        const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(nodes + parent) + 15, 1u);
+        if ((old & 1u) == 0) return;
+        __threadfence();
+        float4* pp = reinterpret_cast<float4*>(nodes + parent);
+        const float4 p0 = __ldcg(pp), p1 = __ldcg(pp + 1), p2 = __ldcg(pp + 2);
+        const uint32_t c0 = wbits(p0), c1 = wbits(p1), up = wbits(p2);
+        const bool     is_left = (c0 == me);
+        const uint32_t sib     = is_left ? c1 : c0;
+        const float4*  sp      = reinterpret_cast<const float4*>(nodes + sib);
+        const float4   s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2), s3 = __ldcg(sp + 3);
+        float3 slo, shi;
+        node_box(s0, s1, s2, s3, sib >= leaf0, slo, shi);
+        if (is_left)
+        {
+            pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up); pp[3] = pack(shi, old + 1u);
+        }
+        else
+        {
+            pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up); pp[3] = pack(hi, old + 1u);
+        }
+        lo = min3(lo, slo);
+        hi = max3(hi, shi);
+        me = parent;
+        parent = up;
+    }
+}
+
+// ---- K8: instance world boxes + scene AABB (lbvh_calc_scene_aabb.comp:131-163, common.h:270-308) -------
+__device__ __forceinline__ float3 transform_point(const float* m, float3 p)
+{
+    return make_float3(((m[0] * p.x + m[1] * p.y) + m[2] * p.z) + m[3], ((m[4] * p.x + m[5] * p.y) + m[6] * p.z) + m[7],
+                       ((m[8] * p.x + m[9] * p.y) + m[10] * p.z) + m[11]);
+}
+
+__global__ void __launch_bounds__(256)
+    k_instance_boxes(const InstanceDesc* __restrict__ descs, uint32_t n, int corner_quirk, float4* __restrict__ boxes,
+                     uint32_t* __restrict__ g_aabb)
+{
+    OrderedBox sb;
+    sb.init();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        const InstanceDesc d  = descs[i];
+        const float4*      rp = reinterpret_cast<const float4*>(d.blas);
+        const float4       q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3];
+        float3 a, b;
+        // A BLAS whose root is a leaf (one triangle) is bounded by its vertices.
+        node_box(q0, q1, q2, q3, wbits(q0) == kInvalid, a, b);
+        float3 c[8];
+        c[0] = a;
+        c[1] = make_float3(a.x, a.y, b.z);
+        c[2] = make_float3(a.x, b.y, a.z);
+        c[3] = make_float3(a.x, b.y, b.z);
+        c[4] = make_float3(b.x, a.y, b.z);
+        c[5] = make_float3(b.x, b.y, a.z);
+        c[6] = corner_quirk ? b : make_float3(b.x, a.y, a.z);  // reference enumerates pmax twice (common.h:288-289)
+        c[7] = b;
+        float3 lo = transform_point(d.m, c[0]), hi = lo;
+#pragma unroll
+        for (int k = 1; k < 8; ++k)
+        {
+            const float3 t = transform_point(d.m, c[k]);
+            lo = min3(lo, t);
+            hi = max3(hi, t);
+        }
+        boxes[2 * (size_t)i]     = make_float4(lo.x, lo.y, lo.z, 0.f);
+        boxes[2 * (size_t)i + 1] = make_float4(hi.x, hi.y, hi.z, 0.f);
+        sb.grow(lo);
+        sb.grow(hi);
+    }
+    reduce_box_to_global(sb, g_aabb);
+}
+
+inline int grid_for(const DeviceInfo& dev, uint32_t n, int threads, int ctas_per_sm)
+{
+    size_t need = ((size_t)n + threads - 1) / threads;
+    return (int)std::max<size_t>(1, std::min<size_t>(need, (size_t)dev.sm_count * ctas_per_sm));
+}
+}  // namespace
+
+// ---- layouts -------------------------------------------------------------------------------------------
+// Build scratch: [aabb_max 16 | sort hist/tickets/status]  <- one memset(0)
+//                [aabb_min 16 | flags 4(N-1)]              <- one memset(0xFF)
+//                codes 4N | sorted codes 4N | sorted refs 4N | sort tmp keys/vals 8N
+// The scene-AABB words are split so that each memset node also initialises the min (all ones) / max (zero)
+// identities of the ordered encoding; g_aabb[0..2]=min, [4..6]=max as in the reference's uint[8].
+BlasLayout blas_layout(uint32_t n, bool restructure)
+{
+    BlasLayout L;
+    L.n    = n;
+    L.sort = sort_layout(n);
+    size_t off = 0;
+    // region A (memset 0xFF): aabb min (16 B) + flags
+    L.aabb_off  = off;              // 32 B: min[4] then max[4]
+    off += 32;
+    L.flags_off = off; off += align_up(sizeof(uint32_t) * (size_t)(n ? n : 1), 256);
+    L.codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
+    L.sorted_codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
+    L.sorted_refs_off  = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
+    L.sort_off = off; off += L.sort.total;
+    L.treelet_off  = 0;
+    L.treelet_size = restructure ? treelet_scratch_size(n) : 0;
+    L.scratch_total = std::max(off, L.treelet_size);
+    L.result_total  = sizeof(Node) * (2 * (size_t)n - 1);
+    return L;
+}
+
+static void reset_build_scratch(cudaStream_t s, char* sc, size_t aabb_off, size_t flags_off, size_t flags_bytes, const SortLayout& sl,
+                                size_t sort_off)
+{
+    // min words + flags -> 0xFF ; max words -> 0 ; sort bookkeeping -> 0
+    RR_CUDA_CHECK(cudaMemsetAsync(sc + aabb_off, 0xFF, 16, s));
+    RR_CUDA_CHECK(cudaMemsetAsync(sc + aabb_off + 16, 0x00, 16, s));
+    RR_CUDA_CHECK(cudaMemsetAsync(sc + flags_off, 0xFF, flags_bytes, s));
+    RR_CUDA_CHECK(cudaMemsetAsync(sc + sort_off + sl.hist_off, 0, sl.tmp_keys_off - sl.hist_off, s));
+}
+
+void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, const BlasLayout& L, void* scratch, Node* nodes,
+                bool restructure)
+{
+    const uint32_t n = mesh.triangle_count;
+    if (n == 0) return;
+    char*     sc           = (char*)scratch;
+    uint32_t* g_aabb       = reinterpret_cast<uint32_t*>(sc + L.aabb_off);
+    uint32_t* flags        = reinterpret_cast<uint32_t*>(sc + L.flags_off);
+    uint32_t* codes        = reinterpret_cast<uint32_t*>(sc + L.codes_off);
+    uint32_t* sorted_codes = reinterpret_cast<uint32_t*>(sc + L.sorted_codes_off);
+    uint32_t* sorted_refs  = reinterpret_cast<uint32_t*>(sc + L.sorted_refs_off);
+    void*     sort_scratch = sc + L.sort_off;
+
+    reset_build_scratch(s, sc, L.aabb_off, L.flags_off, sizeof(uint32_t) * (size_t)n, L.sort, L.sort_off);
+    k_scene_aabb<<<grid_for(dev, n, 256, 8), 256, 0, s>>>(mesh, g_aabb);
+    k_morton<false><<<grid_for(dev, n, 256, 8), 256, 0, s>>>(mesh, nullptr, n, g_aabb, codes, sort_hist_ptr(L.sort, sort_scratch));
+    *dev.launches += 2;
+    sort_pairs(dev, s, L.sort, sort_scratch, codes, nullptr, sorted_codes, sorted_refs);
+    EmitParams p{};
+    p.codes = sorted_codes; p.refs = sorted_refs; p.n = n; p.flags = flags; p.nodes = nodes; p.mesh = mesh;
+    k_emit_fit<false><<<(n + 255) / 256, 256, 0, s>>>(p);
+    ++*dev.launches;
+    RR_CUDA_CHECK(cudaGetLastError());
+    if (restructure) restructure_blas(dev, s, nodes, n, scratch);
+}
+
+void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, Node* nodes)
+{
+    const uint32_t n = mesh.triangle_count;
+    if (n == 0) return;
+    k_refit<<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n);
+    ++*dev.launches;
+    RR_CUDA_CHECK(cudaGetLastError());
+}
+
+// Scene buffer: [nodes (2n-1) x 64 | instance records n x 64 | forward transforms n x 48]
+// (reference: [(2n-1) x 64 | 2n x 48], vlk/hlbvh_top_level_builder.cpp:378-381; the BLAS addresses that the
+// reference binds as a descriptor array live in the records here, so there is no 2048-instance cap).
+SceneLayout scene_layout(uint32_t n)
+{
+    SceneLayout L;
+    L.n    = n;
+    L.sort = sort_layout(n);
+    size_t off = 0;
+    L.nodes_off   = off; off += align_up(sizeof(Node) * (2 * (size_t)(n ? n : 1) - 1), 256);
+    L.records_off = off; off += align_up(sizeof(InstanceRecord) * (size_t)n, 256);
+    L.fwd_off     = off; off += align_up(48 * (size_t)n, 256);
+    L.result_total = off;
+    off = 0;
+    L.aabb_off  = off; off += 32;
+    L.flags_off = off; off += align_up(sizeof(uint32_t) * (size_t)(n ? n : 1), 256);
+    L.desc_off  = off; off += align_up(sizeof(InstanceDesc) * (size_t)n, 256);
+    L.boxes_off = off; off += align_up(32 * (size_t)n, 256);
+    L.codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
+    L.sorted_codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
+    L.sorted_refs_off  = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
+    L.sort_off = off; off += L.sort.total;
+    L.scratch_total = off;
+    return L;
+}
+
+void build_scene(const DeviceInfo& dev, cudaStream_t s, const InstanceDesc* host_descs, const SceneLayout& L, void* scratch, void* scene,
+                 bool corner_quirk)
+{
+    const uint32_t n = L.n;
+    if (n == 0) return;
+    char* sc = (char*)scratch;
+    char* out = (char*)scene;
+    uint32_t*     g_aabb       = reinterpret_cast<uint32_t*>(sc + L.aabb_off);
+    uint32_t*     flags        = reinterpret_cast<uint32_t*>(sc + L.flags_off);
+    InstanceDesc* descs        = reinterpret_cast<InstanceDesc*>(sc + L.desc_off);
+    float4*       boxes        = reinterpret_cast<float4*>(sc + L.boxes_off);
+    uint32_t*     codes        = reinterpret_cast<uint32_t*>(sc + L.codes_off);
+    uint32_t*     sorted_codes = reinterpret_cast<uint32_t*>(sc + L.sorted_codes_off);
+    uint32_t*     sorted_refs  = reinterpret_cast<uint32_t*>(sc + L.sorted_refs_off);
+    void*         sort_scratch = sc + L.sort_off;
+
+    RR_CUDA_CHECK(cudaMemcpyAsync(descs, host_descs, sizeof(InstanceDesc) * (size_t)n, cudaMemcpyHostToDevice, s));
+    reset_build_scratch(s, sc, L.aabb_off, L.flags_off, sizeof(uint32_t) * (size_t)n, L.sort, L.sort_off);
+    k_instance_boxes<<<grid_for(dev, n, 256, 4), 256, 0, s>>>(descs, n, corner_quirk ? 1 : 0, boxes, g_aabb);
+    k_morton<true><<<grid_for(dev, n, 256, 4), 256, 0, s>>>(MeshDesc{}, boxes, n, g_aabb, codes, sort_hist_ptr(L.sort, sort_scratch));
+    *dev.launches += 2;
+    sort_pairs(dev, s, L.sort, sort_scratch, codes, nullptr, sorted_codes, sorted_refs);
+    EmitParams p{};
+    p.codes = sorted_codes; p.refs = sorted_refs; p.n = n; p.flags = flags;
+    p.nodes   = reinterpret_cast<Node*>(out + L.nodes_off);
+    p.boxes   = boxes;
+    p.descs   = descs;
+    p.records = reinterpret_cast<InstanceRecord*>(out + L.records_off);
+    p.fwd     = reinterpret_cast<float4*>(out + L.fwd_off);
+    k_emit_fit<true><<<(n + 255) / 256, 256, 0, s>>>(p);
+    ++*dev.launches;
+    RR_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace rr

@@ -1,0 +1,155 @@
+// rr_internal.h -- shared declarations of the CUDA backend (host runtime <-> kernel launchers).
+//
+// Layering (the analogue of the reference's base/ + vlk/ split):
+//   rr_api.cpp      C ABI shim: null checks -> RR_ERROR_INVALID_PARAMETER, exceptions -> RR_ERROR_INTERNAL
+//   rr_runtime.cpp  context / command stream / event / device pointer objects over the CUDA runtime
+//   rr_build.cu     HLBVH build + refit + TLAS kernels and their launch sequences
+//   rr_sort.cu      onesweep LSD radix sort (stable key-value)
+//   rr_treelet.cu   treelet restructuring
+//   rr_trace.cu     closest / any-hit traversal, one and two level
+// There is no CPU fallback anywhere: every entry point below launches CUDA kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "radeonrays.h"
+
+namespace rr
+{
+constexpr uint32_t kInvalid  = 0xFFFFFFFFu;
+constexpr uint32_t kSentinel = 0xFFFFFFFEu;  // isect_2l.comp RR_TOP_LEVEL_SENTINEL
+
+// 64-byte BVH2 node, identical to the reference's layout (vlk/kernels/bvh2.h:25-35) so that a raw
+// dump of a geometry buffer is a VkBvhNode[] that bvh_analyzer can load (bvh_analyzer/transform.h:31-41).
+//   q0 = (aabb0_min | v0, child0)   q1 = (aabb0_max | v1, child1)
+//   q2 = (aabb1_min | v2, parent)   q3 = (aabb1_max | 0 , update)
+struct alignas(64) Node
+{
+    float4 q0, q1, q2, q3;
+};
+static_assert(sizeof(Node) == 64, "node must be 64 bytes");
+
+// Per-instance record of a scene buffer (64 B, one cache line): inverse transform rows + BLAS base.
+struct alignas(64) InstanceRecord
+{
+    float4          inv0, inv1, inv2;  // object<-world rows (m0, m1, m2 of common.h Transform)
+    const Node*     blas;              // device address of the instance's BLAS node 0
+    unsigned long long pad;
+};
+static_assert(sizeof(InstanceRecord) == 64, "instance record must be 64 bytes");
+
+// Host-side instance description consumed at record time (vlk/intersector.cpp:40-45, 222-247).
+struct InstanceDesc
+{
+    float       m[12];
+    const Node* blas;
+    uint32_t    index;
+    uint32_t    pad;
+};
+static_assert(sizeof(InstanceDesc) == 64, "instance desc must be 64 bytes");
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct CudaError : std::runtime_error
+{
+    cudaError_t code;
+    CudaError(cudaError_t c, const char* what) : std::runtime_error(std::string(what) + ": " + cudaGetErrorString(c)), code(c) {}
+};
+#define RR_CUDA_CHECK(expr)                                                  \
+    do                                                                       \
+    {                                                                        \
+        cudaError_t _e = (expr);                                             \
+        if (_e != cudaSuccess) throw ::rr::CudaError(_e, #expr);             \
+    } while (0)
+
+// ---- launch context handed to every launcher -------------------------------------------------------
+struct DeviceInfo
+{
+    int      device      = 0;
+    int      sm_count    = 148;
+    size_t   l2_bytes    = 0;
+    uint64_t* launches   = nullptr;  // per-context launch counter (host side)
+};
+
+// ---- sort (rr_sort.cu) ------------------------------------------------------------------------------
+struct SortLayout
+{
+    uint32_t n = 0, tiles = 0;
+    size_t   hist_off = 0, counter_off = 0, status_off = 0, tmp_keys_off = 0, tmp_vals_off = 0, total = 0;
+};
+SortLayout sort_layout(uint32_t n);
+// Zeroes histogram / tile counters / look-back status (must precede histogram accumulation).
+void sort_reset(const DeviceInfo& dev, cudaStream_t s, const SortLayout& L, void* scratch);
+// Accumulates the 4x256 digit histograms of keys (skipped when the producer kernel already did).
+void sort_histogram(const DeviceInfo& dev, cudaStream_t s, const SortLayout& L, void* scratch, const uint32_t* keys);
+// 4 onesweep passes. keys_in is clobbered only if it aliases nothing else; result lands in keys_out/vals_out.
+// vals_in == nullptr means "values are 0..n-1" (generated on the fly in the first pass).
+void sort_pairs(const DeviceInfo& dev, cudaStream_t s, const SortLayout& L, void* scratch, uint32_t* keys_in,
+                const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out);
+uint32_t* sort_hist_ptr(const SortLayout& L, void* scratch);
+
+// ---- build (rr_build.cu) ------------------------------------------------------------------------------
+struct MeshDesc
+{
+    const float*    vertices;       // device
+    uint32_t        vertex_count;
+    uint32_t        stride_floats;  // vertex_stride >> 2 (lbvh_calc_mesh_aabb.comp:128)
+    const uint32_t* indices;        // device, 3 per triangle (index_type ignored like the reference)
+    uint32_t        triangle_count;
+};
+struct BlasLayout
+{
+    uint32_t   n = 0;
+    size_t     aabb_off = 0, codes_off = 0, sorted_codes_off = 0, sorted_refs_off = 0, flags_off = 0, sort_off = 0;
+    size_t     treelet_off = 0, treelet_size = 0;
+    SortLayout sort;
+    size_t     scratch_total = 0, result_total = 0;
+};
+BlasLayout blas_layout(uint32_t triangle_count, bool restructure);
+void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, const BlasLayout& L, void* scratch, Node* nodes,
+                bool restructure);
+void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, Node* nodes);
+
+struct SceneLayout
+{
+    uint32_t   n = 0;
+    size_t     nodes_off = 0, records_off = 0, fwd_off = 0, result_total = 0;  // scene buffer
+    size_t     desc_off = 0, boxes_off = 0, aabb_off = 0, codes_off = 0, sorted_codes_off = 0, sorted_refs_off = 0,
+               flags_off = 0, sort_off = 0, scratch_total = 0;                 // temporary buffer
+    SortLayout sort;
+};
+SceneLayout scene_layout(uint32_t instance_count);
+// descs: host array already staged into pinned memory by the caller; copied to scratch on the stream.
+void build_scene(const DeviceInfo& dev, cudaStream_t s, const InstanceDesc* host_descs, const SceneLayout& L, void* scratch,
+                 void* scene, bool reference_corner_quirk);
+
+// ---- treelets (rr_treelet.cu) ---------------------------------------------------------------------------
+size_t treelet_scratch_size(uint32_t n);
+void   restructure_blas(const DeviceInfo& dev, cudaStream_t s, Node* nodes, uint32_t n, void* scratch);
+
+// ---- trace (rr_trace.cu) ----------------------------------------------------------------------------------
+struct TraceArgs
+{
+    const Node*           bvh;          // BLAS (one level) or TLAS nodes (two level)
+    const InstanceRecord* instances;    // nullptr => one level
+    const RRRay*          rays;
+    uint32_t              ray_count;
+    const uint32_t*       indirect_count;  // optional device counter
+    void*                 hits;
+    uint32_t*             scratch;      // spill arena
+    size_t                scratch_bytes;
+    RRIntersectQuery      query;
+    RRIntersectQueryOutput output;
+    bool                  first_found_tie_rule;
+};
+size_t trace_scratch_size(const DeviceInfo& dev, uint32_t ray_count);
+void   trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a);
+
+}  // namespace rr

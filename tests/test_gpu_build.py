@@ -1,0 +1,133 @@
+"""-m gpu: HLBVH build / refit / treelet parity of the CUDA path (through the rr* C ABI) against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import binding as O
+from radeonrays_sdk_b200 import api, workloads as W
+from helpers import assert_nodes_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_build(engine, pos, idx, flags=api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD):
+    g = engine.build_geometry(pos, idx, build_flags=flags)
+    n = idx.shape[0]
+    restructure = flags is not None and not (flags & api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD)
+    want, sc, sr = O.build_blas(pos, idx, restructure=restructure)
+    L = engine.ctx.build_scratch_layout(n)
+    if not restructure:  # treelet scratch aliases the build scratch
+        lo, hi = O.scene_aabb(pos, idx)
+        aabb = g.scratch_u32(L.scene_aabb_offset, 8)
+        dec = lambda v: (v ^ (((v >> 31) - 1) | 0x80000000)).astype(np.uint32).view(np.float32)
+        assert np.array_equal(dec(aabb[0:3]).view(np.uint32), lo.view(np.uint32))
+        assert np.array_equal(dec(aabb[4:7]).view(np.uint32), hi.view(np.uint32))
+        codes = g.scratch_u32(L.morton_codes_offset, n)
+        assert np.array_equal(codes, O.morton_codes(pos, idx, lo, hi)), "Morton codes must be bit-exact"
+        assert np.array_equal(g.scratch_u32(L.sorted_codes_offset, n), sc), "sorted codes"
+        assert np.array_equal(g.scratch_u32(L.sorted_refs_offset, n), sr), "sorted primitive order (stable)"
+    got = g.nodes()
+    assert_nodes_equal(got, want)
+    assert O.check_consistency(got)
+    return g, got
+
+
+def test_single_triangle(engine):
+    pos, idx = W.single_triangle()  # basic_test.h:283-292
+    g, nodes = _check_build(engine, pos, idx)
+    assert nodes.shape[0] == 1 and nodes["child0"][0] == O.INVALID and nodes["parent"][0] == O.INVALID
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 31, 32, 33, 255, 1000])
+def test_small_random_meshes(engine, n):
+    rng = np.random.default_rng(n)
+    pos = rng.random((3 * n, 3), dtype=np.float32)
+    idx = rng.permutation(3 * n).astype(np.uint32).reshape(n, 3)
+    _check_build(engine, pos, idx)
+
+
+def test_cornell_box(engine, cornell):
+    pos, idx, _ = cornell
+    _check_build(engine, pos, idx)
+    _check_build(engine, pos, idx, flags=None)           # build_options == NULL
+    _check_build(engine, pos, idx, flags=0)               # quality build (no-op below 64 triangles)
+
+
+def test_sponza_fast_build(engine, sponza):
+    pos, idx, _ = sponza
+    _check_build(engine, pos, idx)
+
+
+def test_sponza_quality_build_matches_oracle_treelets(engine, sponza):
+    pos, idx, _ = sponza
+    g, nodes = _check_build(engine, pos, idx, flags=0)
+    fast, _, _ = O.build_blas(pos, idx)
+    assert O.sah(nodes) <= O.sah(fast)                   # hlbvh_test.h:417
+
+
+def test_duplicate_and_degenerate_inputs(engine):
+    # all centroids identical (every Morton code equal -> index tie-break everywhere), flat extent (0/0 -> NaN -> 0)
+    n = 777
+    pos = np.zeros((3, 3), np.float32)
+    pos[1] = (1, 0, 0)
+    pos[2] = (0, 1, 0)                                     # z extent is zero
+    idx = np.tile(np.array([[0, 1, 2]], np.uint32), (n, 1))
+    _check_build(engine, pos, idx)
+    # vertex stride larger than 12 bytes
+    rng = np.random.default_rng(5)
+    pos4 = rng.random((300, 4), dtype=np.float32)
+    idx = rng.integers(0, 300, (500, 3)).astype(np.uint32)
+    g = engine.build_geometry(pos4, idx, vertex_stride=16)
+    want, _, _ = O.build_blas(pos4, idx)
+    assert_nodes_equal(g.nodes(), want)
+
+
+def test_update_refit(engine, sponza):
+    """hlbvh_test.h:445-493 UpdateTest: move every vertex by +10 in y, UPDATE, topology untouched."""
+    pos, idx, _ = sponza
+    g = engine.build_geometry(pos, idx)
+    before = g.nodes()
+    moved = pos.copy()
+    moved[:, 1] += np.float32(10.0)
+    for rep in range(2):                                   # twice: the parity rendezvous needs no reset pass
+        engine.update_geometry(g, moved)
+        got = g.nodes()
+        want = O.refit(before, moved, idx)
+        assert_nodes_equal(got, want, what=f"refit #{rep}")
+        assert O.check_consistency(got)
+        for f in ("child0", "child1", "parent"):
+            assert np.array_equal(got[f], before[f])
+
+
+def test_update_after_quality_build(engine, sponza):
+    pos, idx, _ = sponza
+    g = engine.build_geometry(pos, idx, build_flags=0)
+    before = g.nodes()
+    moved = (pos * np.float32(1.5)).astype(np.float32)
+    engine.update_geometry(g, moved)
+    assert_nodes_equal(g.nodes(), O.refit(before, moved, idx))
+
+
+def test_heightfield_1m(engine):
+    """A 1 M-triangle slice of config C5's animated height field: rebuild and refit agree with the oracle."""
+    pos, idx = W.heightfield_mesh(1000, 500, t=0.0)
+    g, nodes = _check_build(engine, pos, idx)
+    pos2, _ = W.heightfield_mesh(1000, 500, t=1.0)
+    engine.update_geometry(g, pos2)
+    assert_nodes_equal(g.nodes(), O.refit(nodes, pos2, idx))
+
+
+def test_sort_pairs_stable(engine):
+    """algos_test.h:322-390 SortTest, plus the value/stability check the reference omits."""
+    import torch
+    rng = np.random.default_rng(0)
+    for n, hi in ((1, 10), (1000, 16), (8192, 1000), (8193, 1 << 30), (1 << 20, 1000), (3_000_001, 0xFFFFFFFF)):
+        keys = rng.integers(0, hi, n, dtype=np.uint64).astype(np.uint32)
+        vals = rng.integers(0, 0xFFFFFFFF, n, dtype=np.uint64).astype(np.uint32)
+        dk, dv = torch.from_numpy(keys.view(np.int32)).cuda(), torch.from_numpy(vals.view(np.int32)).cuda()
+        ok, ov = torch.empty_like(dk), torch.empty_like(dv)
+        api.check(engine.ctx.lib.rrCudaDebugSortPairs(engine.ctx.handle, dk.data_ptr(), dv.data_ptr(), ok.data_ptr(), ov.data_ptr(), n))
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(ok.cpu().numpy().view(np.uint32), keys[order])
+        assert np.array_equal(ov.cpu().numpy().view(np.uint32), vals[order])
+        api.check(engine.ctx.lib.rrCudaDebugSortPairs(engine.ctx.handle, dk.data_ptr(), None, ok.data_ptr(), ov.data_ptr(), n))
+        assert np.array_equal(ov.cpu().numpy().view(np.uint32), order.astype(np.uint32))

@@ -1,0 +1,130 @@
+"""-m gpu: closest / any-hit traversal parity (ids bit-exact, uv 1e-6 relative) through rrCmdIntersect."""
+import numpy as np
+import pytest
+
+from oracle import binding as O
+from radeonrays_sdk_b200 import api, workloads as W
+from helpers import assert_hits_equal
+
+pytestmark = pytest.mark.gpu
+
+CLOSEST, ANY = api.RR_INTERSECT_QUERY_CLOSEST, api.RR_INTERSECT_QUERY_ANY
+FULL, IDS = api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, api.RR_INTERSECT_QUERY_OUTPUT_INSTANCE_ID
+
+
+def _all_modes(engine, g, nodes, rays, what):
+    rng = np.random.default_rng(1)
+    init = np.zeros(rays.shape[0], W.HIT_DTYPE)
+    init["uv"] = rng.random((rays.shape[0], 2), dtype=np.float32)
+    init["prim_id"] = 12345
+    init["inst_id"] = 777
+    for query in (CLOSEST, ANY):
+        got = engine.intersect(g, rays, query, FULL, init_hits=init)
+        want = O.trace(nodes, rays, query, O.OUTPUT_FULL_HIT, init=init)
+        assert_hits_equal(got, want, what=f"{what} q={query} full")
+        got = engine.intersect(g, rays, query, IDS)
+        want = O.trace(nodes, rays, query, O.OUTPUT_INSTANCE_ID)
+        assert np.array_equal(got, want), f"{what} q={query} ids"
+
+
+def test_single_triangle_hit_and_miss(engine):
+    pos, idx = W.single_triangle()
+    g = engine.build_geometry(pos, idx)
+    rays = np.zeros(4, W.RAY_DTYPE)
+    rays["origin"] = [(0, 0, 0), (0, 0, 0), (5, 5, 0), (0, 0, 2)]
+    rays["direction"] = [(0, 0, 1), (0, 0, -1), (0, 0, 1), (0, 0, -1)]
+    rays["min_t"], rays["max_t"] = 0.001, 100000.0
+    _all_modes(engine, g, g.nodes(), rays, "single triangle")
+    hits = engine.intersect(g, rays)
+    assert list(hits["inst_id"]) == [0, O.INVALID, O.INVALID, 0]
+
+
+def test_cornell_1024(engine, cornell):
+    """BASELINE config C1: Cornell box, 1024x1024 primary closest-hit rays."""
+    pos, idx, _ = cornell
+    g = engine.build_geometry(pos, idx)
+    nodes = g.nodes()
+    rays = W.cornell_primary_rays(1024)
+    got = engine.intersect(g, rays)
+    want = O.trace(nodes, rays)
+    assert_hits_equal(got, want, what="cornell 1024^2")
+    bf, _ = O.brute_force(pos, idx, rays[::97])
+    ok = bf["inst_id"] != O.INVALID
+    # exhaustive search agrees except possibly on exact-t ties across a culled subtree (see test_oracle_cpu.py)
+    assert (got["prim_id"][::97][ok] != bf["prim_id"][ok]).sum() <= 2
+    _all_modes(engine, g, nodes, W.cornell_primary_rays(128), "cornell 128^2")
+
+
+@pytest.mark.parametrize("flags", [api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD, 0])
+def test_sponza_primary_640(engine, sponza, flags):
+    """internal_resources_test.h: 640x640 canonical primary rays; fast and quality builds."""
+    pos, idx, _ = sponza
+    g = engine.build_geometry(pos, idx, build_flags=flags)
+    nodes = g.nodes()
+    rays = W.sponza_primary_rays(640, 640)
+    _all_modes(engine, g, nodes, rays, f"sponza flags={flags}")
+
+
+def test_sponza_tie_rules(engine, sponza):
+    pos, idx, _ = sponza
+    g = engine.build_geometry(pos, idx)
+    nodes = g.nodes()
+    rays = W.sponza_primary_rays(512, 512)
+    engine.ctx.set_option(api.RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, 1)
+    try:
+        got = engine.intersect(g, rays)
+    finally:
+        engine.ctx.set_option(api.RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, 0)
+    assert_hits_equal(got, O.trace(nodes, rays, tie=O.TIE_FIRST_FOUND), what="first-found rule")
+
+
+def test_sponza_incoherent_and_secondary(engine, sponza):
+    """BASELINE config C3 shapes at test size: shadow (ANY, ids) and diffuse bounce (CLOSEST, full hit)."""
+    pos, idx, _ = sponza
+    g = engine.build_geometry(pos, idx)
+    nodes = g.nodes()
+    prim = W.sponza_primary_rays(256, 256)
+    hits = engine.intersect(g, prim)
+    shadow = W.shadow_rays(pos, idx, prim, hits, count=100_000)
+    diffuse = W.diffuse_rays(pos, idx, prim, hits, count=100_000)
+    got = engine.intersect(g, shadow, ANY, IDS)
+    assert np.array_equal(got, O.trace(nodes, shadow, O.QUERY_ANY, O.OUTPUT_INSTANCE_ID))
+    assert_hits_equal(engine.intersect(g, diffuse), O.trace(nodes, diffuse), what="diffuse")
+    lo, hi = pos.min(0), pos.max(0)
+    rnd = W.random_rays(200_000, lo, hi)
+    _all_modes(engine, g, nodes, rnd, "random rays")
+
+
+def test_indirect_ray_count_and_ragged_sizes(engine, cornell):
+    pos, idx, _ = cornell
+    g = engine.build_geometry(pos, idx)
+    nodes = g.nodes()
+    for n in (1, 31, 33, 127, 129, 1000):
+        rays = W.cornell_primary_rays(32)[:n]
+        assert_hits_equal(engine.intersect(g, rays), O.trace(nodes, rays), what=f"n={n}")
+    rays = W.cornell_primary_rays(32)
+    init = np.zeros(rays.shape[0], W.HIT_DTYPE)
+    init["inst_id"] = 0xABCD
+    got = engine.intersect(g, rays, init_hits=init, indirect_count=100)   # isect.comp:98-103
+    want = O.trace(nodes, rays[:100], init=init[:100])
+    assert_hits_equal(got[:100], want)
+    assert np.all(got["inst_id"][100:] == 0xABCD)
+
+
+def test_deep_stack_spill(engine):
+    """A degenerate mesh (all Morton codes equal) whose rays defer more nodes than the shared-memory stack holds."""
+    n = 4096
+    rng = np.random.default_rng(3)
+    base = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    pos = np.concatenate([base + np.array([0, 0, 1e-4 * i], np.float32) for i in range(n)]).astype(np.float32)
+    # squash the centroids so that codes collide but every triangle still spans the same footprint
+    idx = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    g = engine.build_geometry(pos, idx)
+    nodes = g.nodes()
+    rays = np.zeros(256, W.RAY_DTYPE)
+    rays["origin"] = np.c_[rng.random(256) * 0.4 + 0.05, rng.random(256) * 0.4 + 0.05, -np.ones(256)]
+    rays["direction"] = (0, 0, 1)
+    rays["min_t"], rays["max_t"] = 0.0, 1000.0
+    got = engine.intersect(g, rays)
+    want, st = O.trace(nodes, rays, want_stats=True)
+    assert_hits_equal(got, want, what="deep stack")
