@@ -16,6 +16,7 @@
 // Roofline: compulsory HBM traffic is 32 B/ray in + 16 B (or 4 B) out; the BVH is L2 resident, so the kernel
 // is bound by L1/L2 latency and issue rate, not HBM.
 #include <algorithm>
+#include <cstdlib>
 
 #include "rr_internal.h"
 
@@ -26,7 +27,7 @@ namespace
 constexpr int kTraceThreads = 128;
 constexpr int kSmemStack    = 32;   // entries per thread kept in shared memory
 constexpr int kSpillStack   = 96;   // further entries per thread in the scratch arena
-constexpr int kCtasPerSm    = 8;
+constexpr int kCtasPerSm    = 12;  // upper bound on resident CTAs per SM used for sizing the grid / spill arena
 
 struct Vec3 { float x, y, z; };
 __device__ __forceinline__ Vec3 v3(float x, float y, float z) { Vec3 r{x, y, z}; return r; }
@@ -133,161 +134,192 @@ struct TraceParams
     const uint32_t*       indirect;
     void*                 hits;
     uint32_t*             arena;
+    uint32_t*             ticket;   // chunk counter, first word of the scratch buffer
     int                   first_found;
 };
 
+// Leaving an instance: restore the world-space ray (isect_2l.comp:279-287) and pop again.
+#define RR_POP_NEXT()                                                         \
+    do                                                                        \
+    {                                                                         \
+        addr = st.pop();                                                      \
+        if (kTwoLevel && addr == kSentinel)                                   \
+        {                                                                     \
+            cur_inst = kInvalid;                                              \
+            cur_bvh  = P.bvh;                                                 \
+            ray.set(v3(r0), v3(r1));                                          \
+            addr = st.pop();                                                  \
+        }                                                                     \
+    } while (0)
+
+// One ray, start to finish: the reference's loop (isect.comp:121-216 / isect_2l.comp:173-287) in its "if-if" shape --
+// every iteration fetches the current node and then either tests its two child boxes and descends / defers, enters
+// an instance, or tests the triangle.  Measured alternatives that were NOT kept (profiles/round1_trace_modes.md):
+// a while-while restructuring (descend until a leaf, then test) was 25-40 % slower on B200, and per-lane ray refill
+// (persistent threads with batched replacement) 20-60 % slower, on coherent and incoherent rays alike.
 template <bool kAny, bool kFullHit, bool kTwoLevel>
-__global__ void __launch_bounds__(kTraceThreads, kCtasPerSm) k_trace(TraceParams P)
+__device__ __forceinline__ void trace_ray(const TraceParams& P, Stack& st, uint32_t gidx)
+{
+    const float4 r0 = __ldg(P.rays + 2 * (size_t)gidx), r1 = __ldg(P.rays + 2 * (size_t)gidx + 1);
+    const float  min_t = r0.w;
+    RayState ray;
+    ray.set(v3(r0), v3(r1));
+    float    closest      = r1.w;
+    uint32_t closest_addr = kInvalid, closest_prim = kInvalid, closest_inst = kInvalid;
+    uint32_t cur_inst     = kInvalid;
+    const Node* cur_bvh   = P.bvh;
+    st.sp = 0;
+    st.push(kInvalid);
+    uint32_t addr = 0;
+    while (addr != kInvalid)
+    {
+        const float4* np = reinterpret_cast<const float4*>(cur_bvh + addr);
+        // all four quads are requested at once: the fourth is dead for leaves, but issuing it after the
+        // leaf/internal branch would put a second dependent load on every internal-node visit
+        const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+        if (wbits(q0) != kInvalid)
+        {
+            float a0, a1, b0, b1;
+            slab(q0, q1, ray, closest, min_t, a0, a1);
+            slab(q2, q3, ray, closest, min_t, b0, b1);
+            const bool t0 = a0 <= a1, t1 = b0 <= b1;
+            if (t0 || t1)
+            {
+                const bool c1first = t1 && (a0 > b0);
+                const uint32_t c0 = wbits(q0), c1 = wbits(q1);
+                uint32_t deferred;
+                if (c1first || !t0) { addr = c1; deferred = c0; }
+                else { addr = c0; deferred = c1; }
+                if (t0 && t1) st.push(deferred);
+                continue;
+            }
+        }
+        else if (kTwoLevel && cur_inst == kInvalid)
+        {   // top-level leaf: enter the instance (isect_2l.comp:231-245)
+            cur_inst = wbits(q1);
+            const InstanceRecord* rec = P.instances + cur_inst;
+            Vec3 oo, od;
+            transform_ray(rec, ray.o, ray.d, oo, od);
+            ray.set(oo, od);
+            cur_bvh = rec->blas;
+            st.push(kSentinel);
+            addr = 0;
+            continue;
+        }
+        else
+        {
+            float t;
+            if (tri_test(ray, min_t, q0, q1, q2, closest, t))
+            {
+                const uint32_t prim = wbits(q1);
+                bool accept = t < closest;
+                if (!kAny && !accept && !P.first_found && t == closest && closest_addr != kInvalid)
+                    accept = kTwoLevel ? (cur_inst < closest_inst || (cur_inst == closest_inst && prim < closest_prim))
+                                       : (prim < closest_prim);
+                if (accept)
+                {
+                    if (kAny)
+                    {   // first accepted triangle in traversal order (isect.comp:181-200)
+                        if (kFullHit)
+                        {
+                            const float2 uv = barycentrics(ray, t, q0, q1, q2);
+                            reinterpret_cast<float4*>(P.hits)[gidx] =
+                                make_float4(uv.x, uv.y, __uint_as_float(kTwoLevel ? cur_inst : 0u), __uint_as_float(prim));
+                        }
+                        else
+                            reinterpret_cast<uint32_t*>(P.hits)[gidx] = kTwoLevel ? cur_inst : prim;
+                        return;
+                    }
+                    closest      = t;
+                    closest_addr = addr;
+                    closest_prim = prim;
+                    closest_inst = cur_inst;
+                }
+            }
+        }
+        RR_POP_NEXT();
+    }
+    if (closest_addr != kInvalid)
+    {
+        if (kFullHit)
+        {
+            const Node* hb = P.bvh;
+            if (kTwoLevel)
+            {
+                const InstanceRecord* rec = P.instances + closest_inst;
+                Vec3 oo, od;
+                transform_ray(rec, v3(r0), v3(r1), oo, od);
+                ray.o = oo; ray.d = od;
+                hb = rec->blas;
+            }
+            const float4* np = reinterpret_cast<const float4*>(hb + closest_addr);
+            const float2  uv = barycentrics(ray, closest, __ldg(np), __ldg(np + 1), __ldg(np + 2));
+            reinterpret_cast<float4*>(P.hits)[gidx] =
+                make_float4(uv.x, uv.y, __uint_as_float(kTwoLevel ? closest_inst : 0u), __uint_as_float(closest_prim));
+        }
+        else
+            reinterpret_cast<uint32_t*>(P.hits)[gidx] = kTwoLevel ? closest_inst : closest_prim;
+    }
+    else
+    {   // miss: only the id word is written (isect.comp:238-245)
+        if (kFullHit) reinterpret_cast<uint32_t*>(P.hits)[4 * (size_t)gidx + 2] = kInvalid;
+        else reinterpret_cast<uint32_t*>(P.hits)[gidx] = kInvalid;
+    }
+}
+#undef RR_POP_NEXT
+
+// Persistent warps pull one 32-ray chunk at a time from a global ticket (P.ticket, zeroed by a memset node before
+// the launch) and trace it to completion.  Against a static warp-stride assignment this removes the end-of-kernel
+// imbalance: +29 % on coherent primary rays, +39 % on shadow rays (profiles/round1_trace_modes.md).
+template <bool kAny, bool kFullHit, bool kTwoLevel>
+__global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(TraceParams P)
 {
     __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
     uint32_t count = P.ray_count;
     if (P.indirect) count = min(count, __ldg(P.indirect));  // isect.comp:98-103
-    const uint32_t warps_total = gridDim.x * (kTraceThreads / 32);
-    const uint32_t warp_global = blockIdx.x * (kTraceThreads / 32) + (threadIdx.x >> 5);
-    const uint32_t lane        = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31;
     Stack st;
     st.smem         = s_stack + threadIdx.x;
     st.spill        = P.arena + (blockIdx.x * kTraceThreads + threadIdx.x);
     st.spill_stride = gridDim.x * kTraceThreads;
-
-    for (uint32_t chunk = warp_global; (uint64_t)chunk * 32 < count; chunk += warps_total)
+    while (true)
     {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(P.ticket, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if ((uint64_t)chunk * 32 >= count) break;
         const uint32_t gidx = chunk * 32 + lane;
-        if (gidx >= count) continue;
-        const float4 r0 = __ldg(P.rays + 2 * (size_t)gidx), r1 = __ldg(P.rays + 2 * (size_t)gidx + 1);
-        const float  min_t = r0.w;
-        RayState ray;
-        ray.set(v3(r0), v3(r1));
-        float    closest      = r1.w;
-        uint32_t closest_addr = kInvalid, closest_prim = kInvalid, closest_inst = kInvalid;
-        uint32_t cur_inst     = kInvalid;
-        const Node* cur_bvh   = P.bvh;
-        st.sp = 0;
-        st.push(kInvalid);
-        uint32_t addr = 0;
-        bool     done = false;
-        while (addr != kInvalid)
-        {
-            const float4* np = reinterpret_cast<const float4*>(cur_bvh + addr);
-            const float4  q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-            if (wbits(q0) != kInvalid)
-            {
-                const float4 q3 = __ldg(np + 3);
-                float a0, a1, b0, b1;
-                slab(q0, q1, ray, closest, min_t, a0, a1);
-                slab(q2, q3, ray, closest, min_t, b0, b1);
-                const bool t0 = a0 <= a1, t1 = b0 <= b1;
-                if (t0 || t1)
-                {
-                    const bool c1first = t1 && (a0 > b0);
-                    const uint32_t c0 = wbits(q0), c1 = wbits(q1);
-                    uint32_t deferred;
-                    if (c1first || !t0) { addr = c1; deferred = c0; }
-                    else { addr = c0; deferred = c1; }
-                    if (t0 && t1) st.push(deferred);
-                    continue;
-                }
-            }
-            else if (kTwoLevel && cur_inst == kInvalid)
-            {   // top-level leaf: enter the instance (isect_2l.comp:231-245)
-                cur_inst = wbits(q1);
-                const InstanceRecord* rec = P.instances + cur_inst;
-                Vec3 oo, od;
-                transform_ray(rec, ray.o, ray.d, oo, od);
-                ray.set(oo, od);
-                cur_bvh = rec->blas;
-                st.push(kSentinel);
-                addr = 0;
-                continue;
-            }
-            else
-            {
-                float t;
-                if (tri_test(ray, min_t, q0, q1, q2, closest, t))
-                {
-                    const uint32_t prim = wbits(q1);
-                    bool accept = t < closest;
-                    if (!kAny && !accept && !P.first_found && t == closest && closest_addr != kInvalid)
-                        accept = kTwoLevel ? (cur_inst < closest_inst || (cur_inst == closest_inst && prim < closest_prim))
-                                           : (prim < closest_prim);
-                    if (accept)
-                    {
-                        if (kAny)
-                        {   // first accepted triangle in traversal order (isect.comp:181-200)
-                            if (kFullHit)
-                            {
-                                const float2 uv = barycentrics(ray, t, q0, q1, q2);
-                                reinterpret_cast<float4*>(P.hits)[gidx] =
-                                    make_float4(uv.x, uv.y, __uint_as_float(kTwoLevel ? cur_inst : 0u), __uint_as_float(prim));
-                            }
-                            else
-                                reinterpret_cast<uint32_t*>(P.hits)[gidx] = kTwoLevel ? cur_inst : prim;
-                            done = true;
-                            break;
-                        }
-                        closest      = t;
-                        closest_addr = addr;
-                        closest_prim = prim;
-                        closest_inst = cur_inst;
-                    }
-                }
-            }
-            addr = st.pop();
-            if (kTwoLevel && addr == kSentinel)
-            {   // leaving the instance: restore the world-space ray (isect_2l.comp:279-287)
-                cur_inst = kInvalid;
-                cur_bvh  = P.bvh;
-                ray.set(v3(r0), v3(r1));
-                addr = st.pop();
-            }
-        }
-        if (done) continue;
-        if (closest_addr != kInvalid)
-        {
-            if (kFullHit)
-            {
-                const Node* hb = P.bvh;
-                if (kTwoLevel)
-                {
-                    const InstanceRecord* rec = P.instances + closest_inst;
-                    Vec3 oo, od;
-                    transform_ray(rec, v3(r0), v3(r1), oo, od);
-                    ray.o = oo; ray.d = od;
-                    hb = rec->blas;
-                }
-                const float4* np = reinterpret_cast<const float4*>(hb + closest_addr);
-                const float2  uv = barycentrics(ray, closest, __ldg(np), __ldg(np + 1), __ldg(np + 2));
-                reinterpret_cast<float4*>(P.hits)[gidx] =
-                    make_float4(uv.x, uv.y, __uint_as_float(kTwoLevel ? closest_inst : 0u), __uint_as_float(closest_prim));
-            }
-            else
-                reinterpret_cast<uint32_t*>(P.hits)[gidx] = kTwoLevel ? closest_inst : closest_prim;
-        }
-        else
-        {   // miss: only the id word is written (isect.comp:238-245)
-            if (kFullHit) reinterpret_cast<uint32_t*>(P.hits)[4 * (size_t)gidx + 2] = kInvalid;
-            else reinterpret_cast<uint32_t*>(P.hits)[gidx] = kInvalid;
-        }
+        if (gidx < count) trace_ray<kAny, kFullHit, kTwoLevel>(P, st, gidx);
     }
 }
 
-inline int trace_grid(const DeviceInfo& dev, uint32_t ray_count)
+// Resident CTAs per SM the persistent grid is sized for (one-level kernels fit 10 at 48 registers, two-level 8).
+// RR_CUDA_TRACE_CTAS_PER_SM overrides it for tuning.
+inline int ctas_per_sm(bool two_level)
+{
+    static int env = [] { const char* e = std::getenv("RR_CUDA_TRACE_CTAS_PER_SM"); return e ? std::atoi(e) : 0; }();
+    const int v = env > 0 ? env : (two_level ? 8 : 10);
+    return std::min(v, kCtasPerSm);
+}
+inline int trace_grid(const DeviceInfo& dev, uint32_t ray_count, int per_sm)
 {
     const size_t need = ((size_t)ray_count + kTraceThreads - 1) / kTraceThreads;
-    return (int)std::max<size_t>(1, std::min<size_t>(need, (size_t)dev.sm_count * kCtasPerSm));
+    return (int)std::max<size_t>(1, std::min<size_t>(need, (size_t)dev.sm_count * per_sm));
 }
 
 template <bool kAny, bool kFullHit, bool kTwoLevel>
 void launch(const DeviceInfo& dev, cudaStream_t s, const TraceParams& P)
 {
-    k_trace<kAny, kFullHit, kTwoLevel><<<trace_grid(dev, P.ray_count), kTraceThreads, 0, s>>>(P);
+    k_trace<kAny, kFullHit, kTwoLevel><<<trace_grid(dev, P.ray_count, ctas_per_sm(kTwoLevel)), kTraceThreads, 0, s>>>(P);
 }
 }  // namespace
 
-// Spill arena: kSpillStack words for every resident thread slot (never more slots than rays).
+// Scratch: [256 B header holding the chunk ticket | spill arena: kSpillStack words for every resident thread slot]
+// (never more slots than rays).
+constexpr size_t kScratchHeader = 256;
 size_t trace_scratch_size(const DeviceInfo& dev, uint32_t ray_count)
 {
-    return (size_t)trace_grid(dev, ray_count) * kTraceThreads * kSpillStack * sizeof(uint32_t);
+    return kScratchHeader + (size_t)trace_grid(dev, ray_count, kCtasPerSm) * kTraceThreads * kSpillStack * sizeof(uint32_t);
 }
 
 void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
@@ -296,7 +328,8 @@ void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
     if (a.scratch_bytes < trace_scratch_size(dev, a.ray_count)) throw std::runtime_error("trace scratch buffer too small");
     TraceParams P;
     P.bvh = a.bvh; P.instances = a.instances; P.rays = reinterpret_cast<const float4*>(a.rays); P.ray_count = a.ray_count;
-    P.indirect = a.indirect_count; P.hits = a.hits; P.arena = a.scratch; P.first_found = a.first_found_tie_rule ? 1 : 0;
+    P.indirect = a.indirect_count; P.hits = a.hits; P.ticket = a.scratch; P.arena = a.scratch + kScratchHeader / sizeof(uint32_t); P.first_found = a.first_found_tie_rule ? 1 : 0;
+    RR_CUDA_CHECK(cudaMemsetAsync(a.scratch, 0, sizeof(uint32_t), s));
     const bool any = a.query == RR_INTERSECT_QUERY_ANY, full = a.output == RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, two = a.instances != nullptr;
     if (!two)
     {
