@@ -227,7 +227,9 @@ RRError rrGetGeometryBuildMemoryRequirements(RRContext context, const RRGeometry
         const BlasLayout L = blas_layout(m.triangle_count, wants_restructure(build_options));
         memory_requirements->result_buffer_size           = L.result_total;
         memory_requirements->temporary_build_buffer_size  = L.scratch_total;
-        memory_requirements->temporary_update_buffer_size = 0;  // refit needs no scratch (vlk backend also reports 0)
+        // work lists of the staged refit (the dx backend reports 4 N, dx/update_hlbvh.cpp:59-63; vlk reports 0).  An update
+        // recorded without a temporary buffer still works, as one slower kernel.
+        memory_requirements->temporary_update_buffer_size = update_scratch_size(m.triangle_count);
     }
     catch (...) { return map_exception(); }
     return RR_SUCCESS;
@@ -259,8 +261,10 @@ RRError rrCmdBuildGeometry(RRContext context, RRBuildOperation build_operation, 
             S(command_stream)->commands.push_back([=](cudaStream_t s) { build_blas(dev, s, m, L, scratch, nodes, restructure); });
         }
         else
-        {   // UPDATE: temporary buffer ignored like the reference (vlk/intersector.cpp:176-204)
-            S(command_stream)->commands.push_back([=](cudaStream_t s) { update_blas(dev, s, m, nodes); });
+        {   // UPDATE: the temporary buffer is optional (the reference's Vulkan backend ignores it, vlk/intersector.cpp:176-204)
+            void*        scratch       = temporary_buffer ? D(temporary_buffer)->ptr() : nullptr;
+            const size_t scratch_bytes = temporary_buffer ? D(temporary_buffer)->bytes_available() : 0;
+            S(command_stream)->commands.push_back([=](cudaStream_t s) { update_blas(dev, s, m, nodes, scratch, scratch_bytes); });
         }
     }
     catch (...) { return map_exception(); }

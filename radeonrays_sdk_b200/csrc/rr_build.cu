@@ -186,6 +186,9 @@ struct EmitParams
     uint32_t        n;
     uint32_t*       flags;   // [n-1], preset to 0xFFFFFFFF: rendezvous word per split position
     Node*           nodes;
+    uint32_t*       pending_count;     // preset to 0: climbers handed from the local to the global kernel
+    uint2*          pending;           // [pending_capacity] (split position, far bound) of each
+    uint32_t        pending_capacity;
     // mesh leaves
     MeshDesc mesh;
     // scene leaves
@@ -230,71 +233,61 @@ __device__ __forceinline__ void affine_inverse(const float* m, float4& r0, float
     r2 = make_float4(r20, r21, r22, -((r20 * tx + r21 * ty) + r22 * tz));
 }
 
-// One thread per leaf.  A thread owns a sorted-key range [l,r] (initially its leaf) and climbs:
-//   * [l,r] is the left child of its parent iff l==0 or (r!=n-1 and delta(r,r+1) > delta(l-1,l)) -- the
-//     parent merges with the neighbour sharing the longer prefix (ties are impossible for a valid radix
-//     tree node because the index-augmented keys are distinct and sorted).
-//   * both children meet at flags[split]; the first to arrive leaves its far bound there and retires, the
-//     second learns the sibling's bound, hence the parent's range [L,R], and emits the parent.
-//   * Karras numbering: a non-root internal node is stored at index R if it is a left child (it IS its
-//     parent's split position) and at L if it is a right child (split+1); the root is 0.  This is exactly
-//     the index FindSpan/FindSplit assign top-down, so child0/child1/parent match the reference bit for bit.
-// Boxes are pure min/max, so fitting in arrival order is bit-exact too.
-template <bool kScene>
-__global__ void __launch_bounds__(256) k_emit_fit(EmitParams p)
-{
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= p.n) return;
-    const uint32_t n = p.n, leaf0 = n - 1;
-    const uint32_t ref = p.refs[j];
-    float3 lo, hi;
-    uint32_t me = leaf0 + j;
-    if (kScene)
-    {   // lbvh_fit_aabb_scene.comp:113-130
-        const float4 bmin = p.boxes[2 * (size_t)ref], bmax = p.boxes[2 * (size_t)ref + 1];
-        lo = xyz(bmin);
-        hi = xyz(bmax);
-        const InstanceDesc d = p.descs[ref];
-        InstanceRecord rec;
-        affine_inverse(d.m, rec.inv0, rec.inv1, rec.inv2);
-        rec.blas = d.blas;
-        rec.pad  = 0;
-        p.records[ref]     = rec;
-        p.fwd[3 * (size_t)ref + 0] = make_float4(d.m[0], d.m[1], d.m[2], d.m[3]);
-        p.fwd[3 * (size_t)ref + 1] = make_float4(d.m[4], d.m[5], d.m[6], d.m[7]);
-        p.fwd[3 * (size_t)ref + 2] = make_float4(d.m[8], d.m[9], d.m[10], d.m[11]);
-        Node* nd = p.nodes + me;
-        nd->q0 = pack(lo, kInvalid);
-        nd->q1 = pack(hi, ref);
-        nd->q2 = pack(lo, kInvalid);
-        nd->q3 = pack(hi, 0u);
-    }
-    else
-    {   // lbvh_fit_aabb_mesh.comp:139-163
-        const uint32_t i0 = p.mesh.indices[3 * (size_t)ref + 0], i1 = p.mesh.indices[3 * (size_t)ref + 1],
-                       i2 = p.mesh.indices[3 * (size_t)ref + 2];
-        const float3 v0 = ld3(p.mesh.vertices + (size_t)i0 * p.mesh.stride_floats);
-        const float3 v1 = ld3(p.mesh.vertices + (size_t)i1 * p.mesh.stride_floats);
-        const float3 v2 = ld3(p.mesh.vertices + (size_t)i2 * p.mesh.stride_floats);
-        lo = min3(min3(v0, v1), v2);
-        hi = max3(max3(v0, v1), v2);
-        Node* nd = p.nodes + me;
-        nd->q0 = pack(v0, kInvalid);
-        nd->q1 = pack(v1, ref);
-        nd->q2 = pack(v2, kInvalid);
-        nd->q3 = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+// Hierarchy emission + box fitting in one pass; every node's 64 bytes are written once.
+//
+// Node numbering (Karras 2012, lbvh_emit_hierarchy_mesh.comp:105-217): internal node i covers a range of sorted leaves
+// that has i at one end; a non-root internal node sits at the RIGHT end of its range if it is a left child (it is its
+// parent's split position) and at the LEFT end if it is a right child (split+1); the root is 0; leaf j is node N-1+j.
+//
+// B200 mapping (two kernels):
+//   k_emit_fit   -- a CTA owns a window of kEmitLeaves consecutive sorted leaves, staged in shared memory.  Every
+//     subtree that lies inside the window also has its internal node indices inside the window, so:
+//       T) thread t determines the range and split of internal node b0+t exactly like the reference's emit kernel
+//          (FindSpan / FindSplit as two binary descents over delta(i,j), shared-memory codes, no divergence); a range
+//          that reaches a leaf outside the window marks the node as "not local";
+//       B) boxes of the local nodes are fitted in rounds (a node fires once both children are ready; leaves are ready
+//          at once): pure min/max, no atomics, no fences, as many rounds as the window's subtrees are deep;
+//       F) finished nodes leave as fully coalesced 16-byte quads (4 lanes per 64-byte node);
+//       H) local roots -- nodes and leaves whose parent is not local, ~2 log2(window) per CTA -- are handed to
+//          k_emit_global as (split position, far bound) pairs.
+//   k_emit_global -- one thread per handed-over node climbs with the classic rendezvous on global words (first arrival
+//     leaves its far bound and retires, second emits the parent), reading sibling boxes back with ld.cg.
+// Keeping the climbs out of k_emit_fit matters: a CTA that waited for its one climber to reach the root held 512 thread
+// slots for ~50 us and the kernel ran 4x slower than its traffic allows (profiles/round1_summary.md).
+constexpr int kEmitLeaves = 512;  // leaves (= threads) per CTA
 
-    uint32_t l = j, r = j;
-    bool is_root = (n == 1);
-    bool is_left = false;
-    if (!is_root) is_left = (l == 0) || (r != n - 1 && delta_adjacent(p.codes, r) > delta_adjacent(p.codes, l - 1));
-    while (!is_root)
+struct EmitSmem
+{
+    float4   box[2 * kEmitLeaves][2];  // (lo, hi) of internal node b0+i at [i], of leaf b0+j at [kEmitLeaves + j]
+    float    leaf[kEmitLeaves][9];     // mesh: v0 v1 v2 of the leaf's triangle
+    uint32_t codes[kEmitLeaves + 2];   // sorted codes of leaves b0-1 .. b1+1
+    uint32_t leaf_ref[kEmitLeaves];
+    uint32_t leaf_parent[kEmitLeaves];
+    uint32_t ic0[kEmitLeaves], ic1[kEmitLeaves], iparent[kEmitLeaves];  // ic0 == INVALID: node not local
+    uint32_t ifar[kEmitLeaves];        // the other end of local node i's range
+    uint8_t  ready[kEmitLeaves];
+};
+
+// The rendezvous protocol on the global words, for a node that is already in memory.  (split, far) identify it: the
+// climber covers [far, split] if it is a left child (far <= split), else [split+1, far].
+template <bool kScene>
+__device__ void global_climb(const EmitParams& p, uint32_t split, uint32_t far)
+{
+    const uint32_t n = p.n, leaf0 = n - 1;
+    bool     is_left = far <= split;
+    uint32_t l = is_left ? far : split + 1, r = is_left ? split : far;
+    uint32_t me = (l == r) ? leaf0 + l : (is_left ? r : l);
+    float3   lo, hi;
     {
-        const uint32_t split = is_left ? r : l - 1;
+        const float4* mp = reinterpret_cast<const float4*>(p.nodes + me);
+        const float4 m0 = __ldcg(mp), m1 = __ldcg(mp + 1), m2 = __ldcg(mp + 2), m3 = __ldcg(mp + 3);
+        node_box(m0, m1, m2, m3, !kScene && me >= leaf0, lo, hi);
+    }
+    while (true)
+    {
         __threadfence();  // publish my node before announcing arrival
         const uint32_t other = atomicExch(&p.flags[split], is_left ? l : r);
-        if (other == kInvalid) return;  // first to arrive: the sibling's thread finishes the parent
+        if (other == kInvalid) break;  // first to arrive: the sibling's climber finishes the parent
         __threadfence();
         uint32_t sib, L, R;
         if (is_left) { L = l; R = other; sib = (split + 1 == R) ? leaf0 + split + 1 : split + 1; }
@@ -303,85 +296,351 @@ __global__ void __launch_bounds__(256) k_emit_fit(EmitParams p)
         const float4 s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2), s3 = __ldcg(sp + 3);
         float3 slo, shi;
         node_box(s0, s1, s2, s3, !kScene && sib >= leaf0, slo, shi);
-
-        is_root = (L == 0 && R == n - 1);
-        bool parent_is_left = false;
-        if (!is_root) parent_is_left = (L == 0) || (R != n - 1 && delta_adjacent(p.codes, R) > delta_adjacent(p.codes, L - 1));
+        const bool is_root        = (L == 0 && R == n - 1);
+        const bool parent_is_left = !is_root && ((L == 0) || (R != n - 1 && delta_adjacent(p.codes, R) > delta_adjacent(p.codes, L - 1)));
         const uint32_t parent = is_root ? 0u : (parent_is_left ? R : L);
-        Node* pn = p.nodes + parent;
+        float4* pn = reinterpret_cast<float4*>(p.nodes + parent);
         if (is_left)
         {
-            pn->q0 = pack(lo, me);
-            pn->q1 = pack(hi, sib);
-            pn->q2 = pack(slo, kInvalid);
-            pn->q3 = pack(shi, 0u);
+            pn[0] = pack(lo, me); pn[1] = pack(hi, sib); pn[2] = pack(slo, kInvalid); pn[3] = pack(shi, 0u);
         }
         else
         {
-            pn->q0 = pack(slo, sib);
-            pn->q1 = pack(shi, me);
-            pn->q2 = pack(lo, kInvalid);
-            pn->q3 = pack(hi, 0u);
+            pn[0] = pack(slo, sib); pn[1] = pack(shi, me); pn[2] = pack(lo, kInvalid); pn[3] = pack(hi, 0u);
         }
         reinterpret_cast<uint32_t*>(p.nodes + me)[11]  = parent;  // q2.w = parent
         reinterpret_cast<uint32_t*>(p.nodes + sib)[11] = parent;
         lo = min3(lo, slo);
         hi = max3(hi, shi);
-        l = L; r = R; me = parent; is_left = parent_is_left;
+        l = L; r = R; me = parent;
+        if (is_root) break;  // its parent word is already INVALID
+        is_left = parent_is_left;
+        split   = is_left ? r : l - 1;
     }
-    // root (also the N==1 leaf): parent = INVALID
-    reinterpret_cast<uint32_t*>(p.nodes + me)[11] = kInvalid;
+}
+
+template <bool kScene>
+__global__ void __launch_bounds__(kEmitLeaves, 3) k_emit_fit(EmitParams p)
+{
+    extern __shared__ __align__(16) unsigned char emit_smem_raw[];
+    EmitSmem& S = *reinterpret_cast<EmitSmem*>(emit_smem_raw);
+    __shared__ uint32_t s_pending_n, s_pending_base;
+    const int      n = (int)p.n, leaf0 = n - 1;
+    const int      tid = threadIdx.x;
+    const int      b0  = blockIdx.x * kEmitLeaves;
+    const int      cnt = min(kEmitLeaves, n - b0);
+    const int      b1  = b0 + cnt - 1;
+    const bool     valid = tid < cnt;
+
+    for (int i = tid; i < cnt + 2; i += kEmitLeaves)
+    {
+        const int gi = b0 + i;  // leaf index + 1
+        S.codes[i]   = (gi >= 1 && gi <= n) ? p.codes[gi - 1] : 0u;
+    }
+    if (tid == 0) s_pending_n = 0;
+    S.ic0[tid]         = kInvalid;
+    S.iparent[tid]     = kInvalid;
+    S.leaf_parent[tid] = kInvalid;
+    S.ready[tid]       = 0;
+
+    // ---- leaves: gather, keep for the flush, publish their boxes ---------------------------------------------------
+    if (valid)
+    {
+        const uint32_t ref = p.refs[b0 + tid];
+        S.leaf_ref[tid]    = ref;
+        float3 lo, hi;
+        if (kScene)
+        {   // lbvh_fit_aabb_scene.comp:113-130
+            const float4 bmin = p.boxes[2 * (size_t)ref], bmax = p.boxes[2 * (size_t)ref + 1];
+            lo = xyz(bmin);
+            hi = xyz(bmax);
+            const InstanceDesc d = p.descs[ref];
+            InstanceRecord rec;
+            affine_inverse(d.m, rec.inv0, rec.inv1, rec.inv2);
+            rec.blas = d.blas;
+            rec.pad  = 0;
+            p.records[ref]             = rec;
+            p.fwd[3 * (size_t)ref + 0] = make_float4(d.m[0], d.m[1], d.m[2], d.m[3]);
+            p.fwd[3 * (size_t)ref + 1] = make_float4(d.m[4], d.m[5], d.m[6], d.m[7]);
+            p.fwd[3 * (size_t)ref + 2] = make_float4(d.m[8], d.m[9], d.m[10], d.m[11]);
+        }
+        else
+        {   // lbvh_fit_aabb_mesh.comp:139-163
+            const uint32_t i0 = p.mesh.indices[3 * (size_t)ref + 0], i1 = p.mesh.indices[3 * (size_t)ref + 1],
+                           i2 = p.mesh.indices[3 * (size_t)ref + 2];
+            const float3 v0 = ld3(p.mesh.vertices + (size_t)i0 * p.mesh.stride_floats);
+            const float3 v1 = ld3(p.mesh.vertices + (size_t)i1 * p.mesh.stride_floats);
+            const float3 v2 = ld3(p.mesh.vertices + (size_t)i2 * p.mesh.stride_floats);
+            float* v = S.leaf[tid];
+            v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v1.x; v[4] = v1.y; v[5] = v1.z; v[6] = v2.x; v[7] = v2.y; v[8] = v2.z;
+            lo = min3(min3(v0, v1), v2);
+            hi = max3(max3(v0, v1), v2);
+        }
+        S.box[kEmitLeaves + tid][0] = make_float4(lo.x, lo.y, lo.z, 0.f);
+        S.box[kEmitLeaves + tid][1] = make_float4(hi.x, hi.y, hi.z, 0.f);
+    }
+    __syncthreads();
+
+    // delta(i,j) of lbvh_emit_hierarchy_mesh.comp:85-103 for leaves inside [b0-1, b1+1] (up to a monotone map: true clz)
+    auto delta = [&](int i, int j) -> int {
+        const uint32_t x = S.codes[i + 1 - b0] ^ S.codes[j + 1 - b0];
+        return x ? __clz(x) : 32 + __clz((uint32_t)(i ^ j));
+    };
+
+    // ---- T: range and split of internal node i = b0 + tid (FindSpan / FindSplit, :105-168) --------------------------
+    const int i = b0 + tid;
+    bool      local = false, node_is_left = false;
+    int       far_end = i;
+    uint32_t  c0 = kInvalid, c1 = kInvalid;
+    if (valid && i < n - 1)
+    {
+        const int d_next = delta(i, i + 1);
+        const int d_prev = i > 0 ? delta(i, i - 1) : -1;
+        const int d      = d_next > d_prev ? 1 : -1;
+        const int dmin   = d > 0 ? d_prev : d_next;
+        // furthest leaf this node may reach: the window's guard leaf (b0-1 or b1+1) if it exists, else the array end
+        const int reach = d > 0 ? min(b1 + 1, n - 1) - i : i - max(b0 - 1, 0);
+        int l = 0;
+#pragma unroll
+        for (int t = kEmitLeaves; t >= 1; t >>= 1)
+            if (l + t <= reach && delta(i, i + (l + t) * d) > dmin) l += t;
+        const int j = i + l * d;
+        local       = j >= b0 && j <= b1;
+        if (local)
+        {
+            const int dnode = delta(i, j);
+            int       sp    = 0;
+#pragma unroll
+            for (int t = kEmitLeaves / 2; t >= 1; t >>= 1)
+                if (sp + t < l && delta(i, i + (sp + t) * d) > dnode) sp += t;
+            const int gamma = i + sp * d + min(d, 0);
+            const int lo_end = min(i, j), hi_end = max(i, j);
+            c0 = lo_end == gamma ? (uint32_t)(leaf0 + gamma) : (uint32_t)gamma;
+            c1 = hi_end == gamma + 1 ? (uint32_t)(leaf0 + gamma + 1) : (uint32_t)(gamma + 1);
+            S.ic0[tid]  = c0;
+            S.ic1[tid]  = c1;
+            S.ifar[tid] = (uint32_t)j;
+            far_end      = j;
+            node_is_left = j < i;  // i is the right end of its range
+            if (c0 >= (uint32_t)leaf0) S.leaf_parent[c0 - leaf0 - b0] = (uint32_t)i; else S.iparent[c0 - b0] = (uint32_t)i;
+            if (c1 >= (uint32_t)leaf0) S.leaf_parent[c1 - leaf0 - b0] = (uint32_t)i; else S.iparent[c1 - b0] = (uint32_t)i;
+        }
+    }
+    __syncthreads();
+
+    // ---- B: fit the local nodes bottom-up in rounds ---------------------------------------------------------------
+    {
+        const int  k0 = c0 >= (uint32_t)leaf0 ? kEmitLeaves + (int)(c0 - leaf0) - b0 : (int)c0 - b0;
+        const int  k1 = c1 >= (uint32_t)leaf0 ? kEmitLeaves + (int)(c1 - leaf0) - b0 : (int)c1 - b0;
+        const bool leaf_c0 = c0 >= (uint32_t)leaf0, leaf_c1 = c1 >= (uint32_t)leaf0;
+        bool todo = local;
+        while (true)
+        {
+            bool fire = false;
+            if (todo) fire = (leaf_c0 || S.ready[k0]) && (leaf_c1 || S.ready[k1]);
+            if (fire)
+            {
+                const float4 alo = S.box[k0][0], ahi = S.box[k0][1], blo = S.box[k1][0], bhi = S.box[k1][1];
+                S.box[tid][0] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
+                S.box[tid][1] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+            }
+            // the barrier separates this round's reads of ready[] from the writes below
+            if (__syncthreads_count(fire) == 0) break;
+            if (fire) { S.ready[tid] = 1; todo = false; }
+            __syncthreads();
+        }
+    }
+
+    // ---- F: flush, four coalesced 16-byte quads per node -------------------------------------------------------------
+    for (int q = tid; q < 4 * cnt; q += kEmitLeaves)
+    {
+        const int i2 = q >> 2, part = q & 3;
+        float4    out;
+        if (kScene)
+        {
+            const float4 b = S.box[kEmitLeaves + i2][part & 1];
+            out = make_float4(b.x, b.y, b.z, __uint_as_float(part == 0 ? kInvalid : part == 1 ? S.leaf_ref[i2] : part == 2 ? S.leaf_parent[i2] : 0u));
+        }
+        else if (part == 3) out = make_float4(0.f, 0.f, 0.f, 0.f);
+        else
+        {
+            const float* b = S.leaf[i2] + 3 * part;
+            out = make_float4(b[0], b[1], b[2], __uint_as_float(part == 0 ? kInvalid : part == 1 ? S.leaf_ref[i2] : S.leaf_parent[i2]));
+        }
+        reinterpret_cast<float4*>(p.nodes + leaf0 + b0)[q] = out;
+    }
+    for (int q = tid; q < 4 * cnt; q += kEmitLeaves)
+    {
+        const int      i2 = q >> 2, part = q & 3;
+        const uint32_t a0 = S.ic0[i2];
+        if (a0 == kInvalid) continue;  // not formed inside this window
+        const uint32_t a1 = S.ic1[i2];
+        const uint32_t c  = part < 2 ? a0 : a1;
+        const int      k  = c >= (uint32_t)leaf0 ? kEmitLeaves + (int)(c - leaf0) - b0 : (int)c - b0;
+        const float4   b  = S.box[k][part & 1];
+        const uint32_t w  = part == 0 ? a0 : part == 1 ? a1 : part == 2 ? S.iparent[i2] : 0u;
+        reinterpret_cast<float4*>(p.nodes + b0)[q] = make_float4(b.x, b.y, b.z, __uint_as_float(w));
+    }
+    if (n <= kEmitLeaves) return;  // the whole tree was local
+
+    // ---- H: hand the local roots (parent not in this window) to k_emit_global ----------------------------------------
+    // internal node i covering [far_end, i] (left child) or [i, far_end] (right child); leaf j covering [j, j]
+    const bool has_a = local && S.iparent[tid] == kInvalid;
+    const bool has_b = valid && S.leaf_parent[tid] == kInvalid;
+    uint2      ent_a = make_uint2(0, 0), ent_b = make_uint2(0, 0);
+    if (has_a) ent_a = node_is_left ? make_uint2((uint32_t)i, (uint32_t)far_end) : make_uint2((uint32_t)(i - 1), (uint32_t)far_end);
+    if (has_b)
+    {
+        const bool left = (i == 0) || (i != n - 1 && delta(i, i + 1) > delta(i, i - 1));
+        ent_b = make_uint2((uint32_t)(left ? i : i - 1), (uint32_t)i);
+    }
+    const uint32_t idx_a = has_a ? atomicAdd(&s_pending_n, 1u) : 0u;
+    const uint32_t idx_b = has_b ? atomicAdd(&s_pending_n, 1u) : 0u;
+    __syncthreads();
+    if (tid == 0) s_pending_base = s_pending_n ? atomicAdd(p.pending_count, s_pending_n) : 0u;
+    __syncthreads();
+    const bool fits = s_pending_base + s_pending_n <= p.pending_capacity;
+    if (!fits)
+    {   // list full (never seen: it holds n/4 entries and a window hands over ~2 log2(512)): finish the climbs here
+        __threadfence();
+        __syncthreads();
+    }
+    if (has_a)
+    {
+        if (fits) p.pending[s_pending_base + idx_a] = ent_a;
+        else global_climb<kScene>(p, ent_a.x, ent_a.y);
+    }
+    if (has_b)
+    {
+        if (fits) p.pending[s_pending_base + idx_b] = ent_b;
+        else global_climb<kScene>(p, ent_b.x, ent_b.y);
+    }
+}
+
+// Climbers whose sibling lies outside their window: (split, far bound) identifies the node and its range.
+template <bool kScene>
+__global__ void __launch_bounds__(128) k_emit_global(EmitParams p)
+{
+    const uint32_t count = min(*p.pending_count, p.pending_capacity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        const uint2 e = p.pending[i];
+        global_climb<kScene>(p, e.x, e.y);
+    }
 }
 
 // ---- K6: refit / update (lbvh_fit_aabb_mesh.comp with UPDATE_KERNEL, vlk/update_hlbvh.cpp:118-185) ----
-// Topology untouched.  The rendezvous counter is the node's own `update` word used as a parity bit
-// (atomicAdd; even = first arrival), so no reset pass and no scratch are needed -- the reference's
-// reset kernel covers only the first 1024 primitives.
-__global__ void __launch_bounds__(256) k_refit(MeshDesc m, Node* __restrict__ nodes, uint32_t n)
+// Topology untouched (it may be a treelet-restructured tree, so nothing is assumed about node numbering).  The
+// rendezvous counter is the node's own `update` word used as a parity bit (atomicAdd; even = first arrival), so no
+// reset pass is needed -- the reference's reset kernel covers only the first 1024 primitives.
+//
+// Three stages.  A thread that is still climbing after `max_levels` parents appends the node it just finished to a
+// work list and retires; the next stage resumes from the list.  Stage 1 (one thread per leaf, 3 levels) does 7/8 of
+// the node writes with short-lived CTAs, stage 2 (6 levels) most of the rest, stage 3 the O(n/512) long climbs to the
+// root.  In a single kernel every CTA stayed resident until its one long climber reached the root and the SMs ran
+// mostly empty (8.2 ms for 50 M triangles, 16 % of the HBM roofline).
+struct RefitLists
 {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    uint32_t* count_a;   // stage 1 -> 2
+    uint32_t* items_a;
+    uint32_t* count_b;   // stage 2 -> 3
+    uint32_t* items_b;
+    uint32_t  capacity;  // of each list
+};
+
+template <bool kFromLeaves>
+__global__ void __launch_bounds__(256)
+    k_refit(MeshDesc m, Node* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ in_count, const uint32_t* __restrict__ in_items,
+            uint32_t max_levels, uint32_t* __restrict__ out_count, uint32_t* __restrict__ out_items, uint32_t capacity)
+{
+    __shared__ uint32_t s_list[256];
+    __shared__ uint32_t s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
     const uint32_t leaf0 = n - 1;
-    uint32_t me = leaf0 + j;
-    float4* np = reinterpret_cast<float4*>(nodes + me);
-    const float4 q1 = np[1], q2 = np[2];
-    const uint32_t prim = wbits(q1);
-    uint32_t parent = wbits(q2);
-    const uint32_t i0 = m.indices[3 * (size_t)prim + 0], i1 = m.indices[3 * (size_t)prim + 1], i2 = m.indices[3 * (size_t)prim + 2];
-    const float3 v0 = ld3(m.vertices + (size_t)i0 * m.stride_floats);
-    const float3 v1 = ld3(m.vertices + (size_t)i1 * m.stride_floats);
-    const float3 v2 = ld3(m.vertices + (size_t)i2 * m.stride_floats);
-    np[0] = pack(v0, kInvalid);
-    np[1] = pack(v1, prim);
-    np[2] = pack(v2, parent);
-    float3 lo = min3(min3(v0, v1), v2), hi = max3(max3(v0, v1), v2);
-    while (parent != kInvalid)
+    const uint32_t total = kFromLeaves ? n : min(*in_count, capacity);
+    // every thread runs the same number of rounds so that the hand-over barriers below are uniform
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x)
     {
-        __threadfence();
-        const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(nodes + parent) + 15, 1u);
-        if ((old & 1u) == 0) return;
-        __threadfence();
-        float4* pp = reinterpret_cast<float4*>(nodes + parent);
-        const float4 p0 = __ldcg(pp), p1 = __ldcg(pp + 1), p2 = __ldcg(pp + 2);
-        const uint32_t c0 = wbits(p0), c1 = wbits(p1), up = wbits(p2);
-        const bool     is_left = (c0 == me);
-        const uint32_t sib     = is_left ? c1 : c0;
-        const float4*  sp      = reinterpret_cast<const float4*>(nodes + sib);
-        const float4   s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2), s3 = __ldcg(sp + 3);
-        float3 slo, shi;
-        node_box(s0, s1, s2, s3, sib >= leaf0, slo, shi);
-        if (is_left)
+        const uint32_t j = base + threadIdx.x;
+        if (j < total)
         {
-            pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up); pp[3] = pack(shi, old + 1u);
+            uint32_t me, parent;
+            float3   lo, hi;
+            if (kFromLeaves)
+            {
+                me = leaf0 + j;
+                float4* np = reinterpret_cast<float4*>(nodes + me);
+                const float4 q1 = np[1], q2 = np[2];
+                const uint32_t prim = wbits(q1);
+                parent = wbits(q2);
+                const uint32_t i0 = m.indices[3 * (size_t)prim + 0], i1 = m.indices[3 * (size_t)prim + 1], i2 = m.indices[3 * (size_t)prim + 2];
+                const float3 v0 = ld3(m.vertices + (size_t)i0 * m.stride_floats);
+                const float3 v1 = ld3(m.vertices + (size_t)i1 * m.stride_floats);
+                const float3 v2 = ld3(m.vertices + (size_t)i2 * m.stride_floats);
+                np[0] = pack(v0, kInvalid);
+                np[1] = pack(v1, prim);
+                np[2] = pack(v2, parent);
+                lo = min3(min3(v0, v1), v2);
+                hi = max3(max3(v0, v1), v2);
+            }
+            else
+            {
+                me = in_items[j];
+                const float4* np = reinterpret_cast<const float4*>(nodes + me);
+                const float4 q0 = __ldcg(np), q1 = __ldcg(np + 1), q2 = __ldcg(np + 2), q3 = __ldcg(np + 3);
+                node_box(q0, q1, q2, q3, false, lo, hi);
+                parent = wbits(q2);
+            }
+            uint32_t level = 0;
+            while (parent != kInvalid)
+            {
+                if (level == max_levels)
+                {   // hand over: `me` is complete, its rendezvous at `parent` is the next stage's first step
+                    s_list[atomicAdd(&s_n, 1u)] = me;
+                    break;
+                }
+                __threadfence();
+                const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(nodes + parent) + 15, 1u);
+                if ((old & 1u) == 0) break;
+                __threadfence();
+                float4* pp = reinterpret_cast<float4*>(nodes + parent);
+                const float4 p0 = __ldcg(pp), p1 = __ldcg(pp + 1), p2 = __ldcg(pp + 2);
+                const uint32_t c0 = wbits(p0), c1 = wbits(p1), up = wbits(p2);
+                const bool     is_left = (c0 == me);
+                const uint32_t sib     = is_left ? c1 : c0;
+                const float4*  sp      = reinterpret_cast<const float4*>(nodes + sib);
+                const float4   s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2), s3 = __ldcg(sp + 3);
+                float3 slo, shi;
+                node_box(s0, s1, s2, s3, sib >= leaf0, slo, shi);
+                if (is_left)
+                {
+                    pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up); pp[3] = pack(shi, old + 1u);
+                }
+                else
+                {
+                    pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up); pp[3] = pack(hi, old + 1u);
+                }
+                lo = min3(lo, slo);
+                hi = max3(hi, shi);
+                me = parent;
+                parent = up;
+                ++level;
+            }
         }
-        else
+        if (out_items)
         {
-            pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up); pp[3] = pack(hi, old + 1u);
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                s_base = s_n ? atomicAdd(out_count, s_n) : 0u;
+            }
+            __syncthreads();
+            if (threadIdx.x < s_n && s_base + threadIdx.x < capacity) out_items[s_base + threadIdx.x] = s_list[threadIdx.x];
+            __syncthreads();
+            if (threadIdx.x == 0) s_n = 0;
+            __syncthreads();
         }
-        lo = min3(lo, slo);
-        hi = max3(hi, shi);
-        me = parent;
-        parent = up;
     }
 }
 
@@ -432,6 +691,23 @@ __global__ void __launch_bounds__(256)
     reduce_box_to_global(sb, g_aabb);
 }
 
+template <bool kScene>
+void launch_emit_fit(cudaStream_t s, const EmitParams& p)
+{
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        RR_CUDA_CHECK(cudaFuncSetAttribute(k_emit_fit<kScene>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem)));
+        attr_set = true;
+    }
+    k_emit_fit<kScene><<<(p.n + kEmitLeaves - 1) / kEmitLeaves, kEmitLeaves, sizeof(EmitSmem), s>>>(p);
+    if (p.n > (uint32_t)kEmitLeaves)
+    {
+        const uint32_t threads = std::min<uint32_t>(p.pending_capacity, 148u * 16u * 128u);
+        k_emit_global<kScene><<<(threads + 127) / 128, 128, 0, s>>>(p);
+    }
+}
+
 inline int grid_for(const DeviceInfo& dev, uint32_t n, int threads, int ctas_per_sm)
 {
     size_t need = ((size_t)n + threads - 1) / threads;
@@ -445,6 +721,10 @@ inline int grid_for(const DeviceInfo& dev, uint32_t n, int threads, int ctas_per
 //                codes 4N | sorted codes 4N | sorted refs 4N | sort tmp keys/vals 8N
 // The scene-AABB words are split so that each memset node also initialises the min (all ones) / max (zero)
 // identities of the ordered encoding; g_aabb[0..2]=min, [4..6]=max as in the reference's uint[8].
+// Hand-over list between k_emit_fit and k_emit_global: ~2 log2(window) entries per 512-leaf window in practice
+// (1 % of n); n/4 leaves a wide margin and a full list only makes the CTA finish its climbs itself.
+static uint32_t emit_pending_capacity(uint32_t n) { return n <= (uint32_t)kEmitLeaves ? 0u : std::max<uint32_t>(1024u, n / 4); }
+
 BlasLayout blas_layout(uint32_t n, bool restructure)
 {
     BlasLayout L;
@@ -459,6 +739,8 @@ BlasLayout blas_layout(uint32_t n, bool restructure)
     L.sorted_codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sorted_refs_off  = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sort_off = off; off += L.sort.total;
+    L.pending_capacity = emit_pending_capacity(n);
+    L.pending_off = off; off += align_up(sizeof(uint2) * (size_t)L.pending_capacity, 256);
     L.treelet_off  = 0;
     L.treelet_size = restructure ? treelet_scratch_size(n) : 0;
     L.scratch_total = std::max(off, L.treelet_size);
@@ -496,18 +778,49 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
     sort_pairs(dev, s, L.sort, sort_scratch, codes, nullptr, sorted_codes, sorted_refs);
     EmitParams p{};
     p.codes = sorted_codes; p.refs = sorted_refs; p.n = n; p.flags = flags; p.nodes = nodes; p.mesh = mesh;
-    k_emit_fit<false><<<(n + 255) / 256, 256, 0, s>>>(p);
-    ++*dev.launches;
+    p.pending_count = g_aabb + 7;  // spare word of the scene-AABB block, zeroed with the max half
+    p.pending = reinterpret_cast<uint2*>(sc + L.pending_off); p.pending_capacity = L.pending_capacity;
+    launch_emit_fit<false>(s, p);
+    *dev.launches += n > (uint32_t)kEmitLeaves ? 2 : 1;
     RR_CUDA_CHECK(cudaGetLastError());
     if (restructure) restructure_blas(dev, s, nodes, n, scratch);
 }
 
-void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, Node* nodes)
+// Update scratch: [256 B: the two list counters | list A 4 x capacity | list B 4 x capacity], capacity = n/4 + 256:
+// a hand-over after k levels implies a finished subtree of >= k+1 leaves, so stage 1 (3 levels) emits <= n/4 entries.
+size_t update_scratch_size(uint32_t n)
+{
+    const size_t cap = (size_t)n / 4 + 256;
+    return 256 + 2 * align_up(sizeof(uint32_t) * cap, 256);
+}
+
+void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, Node* nodes, void* scratch, size_t scratch_bytes)
 {
     const uint32_t n = mesh.triangle_count;
     if (n == 0) return;
-    k_refit<<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n);
-    ++*dev.launches;
+    const uint32_t kUnbounded = 0xFFFFFFFFu;
+    if (n < 4096 || !scratch || scratch_bytes < update_scratch_size(n))
+    {   // small mesh, or a client that passes no temporary buffer for updates (the Vulkan backend reports 0 bytes)
+        k_refit<true><<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n, nullptr, nullptr, kUnbounded, nullptr, nullptr, 0);
+        ++*dev.launches;
+        RR_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
+    char*          sc  = (char*)scratch;
+    const uint32_t cap = n / 4 + 256;
+    RefitLists L;
+    L.count_a = reinterpret_cast<uint32_t*>(sc);
+    L.count_b = L.count_a + 1;
+    L.items_a = reinterpret_cast<uint32_t*>(sc + 256);
+    L.items_b = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (size_t)cap, 256));
+    L.capacity = cap;
+    RR_CUDA_CHECK(cudaMemsetAsync(sc, 0, 8, s));
+    k_refit<true><<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n, nullptr, nullptr, 3u, L.count_a, L.items_a, cap);
+    const uint32_t grid2 = std::min<uint32_t>((cap + 255) / 256, (uint32_t)dev.sm_count * 64u);
+    k_refit<false><<<grid2, 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, 6u, L.count_b, L.items_b, cap);
+    const uint32_t grid3 = std::min<uint32_t>((cap / 64 + 255) / 256 + 1, (uint32_t)dev.sm_count * 16u);
+    k_refit<false><<<grid3, 256, 0, s>>>(mesh, nodes, n, L.count_b, L.items_b, kUnbounded, nullptr, nullptr, cap);
+    *dev.launches += 3;
     RR_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -533,6 +846,8 @@ SceneLayout scene_layout(uint32_t n)
     L.sorted_codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sorted_refs_off  = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sort_off = off; off += L.sort.total;
+    L.pending_capacity = emit_pending_capacity(n);
+    L.pending_off = off; off += align_up(sizeof(uint2) * (size_t)L.pending_capacity, 256);
     L.scratch_total = off;
     return L;
 }
@@ -566,8 +881,10 @@ void build_scene(const DeviceInfo& dev, cudaStream_t s, const InstanceDesc* host
     p.descs   = descs;
     p.records = reinterpret_cast<InstanceRecord*>(out + L.records_off);
     p.fwd     = reinterpret_cast<float4*>(out + L.fwd_off);
-    k_emit_fit<true><<<(n + 255) / 256, 256, 0, s>>>(p);
-    ++*dev.launches;
+    p.pending_count = g_aabb + 7;
+    p.pending = reinterpret_cast<uint2*>(sc + L.pending_off); p.pending_capacity = L.pending_capacity;
+    launch_emit_fit<true>(s, p);
+    *dev.launches += n > (uint32_t)kEmitLeaves ? 2 : 1;
     RR_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -107,7 +107,8 @@ struct MeshDesc
 struct BlasLayout
 {
     uint32_t   n = 0;
-    size_t     aabb_off = 0, codes_off = 0, sorted_codes_off = 0, sorted_refs_off = 0, flags_off = 0, sort_off = 0;
+    size_t     aabb_off = 0, codes_off = 0, sorted_codes_off = 0, sorted_refs_off = 0, flags_off = 0, sort_off = 0, pending_off = 0;
+    uint32_t   pending_capacity = 0;
     size_t     treelet_off = 0, treelet_size = 0;
     SortLayout sort;
     size_t     scratch_total = 0, result_total = 0;
@@ -115,14 +116,17 @@ struct BlasLayout
 BlasLayout blas_layout(uint32_t triangle_count, bool restructure);
 void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, const BlasLayout& L, void* scratch, Node* nodes,
                 bool restructure);
-void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, Node* nodes);
+size_t update_scratch_size(uint32_t triangle_count);
+// scratch may be null / too small: the refit then runs as one kernel without work lists (slower on large meshes).
+void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, Node* nodes, void* scratch, size_t scratch_bytes);
 
 struct SceneLayout
 {
     uint32_t   n = 0;
     size_t     nodes_off = 0, records_off = 0, fwd_off = 0, result_total = 0;  // scene buffer
     size_t     desc_off = 0, boxes_off = 0, aabb_off = 0, codes_off = 0, sorted_codes_off = 0, sorted_refs_off = 0,
-               flags_off = 0, sort_off = 0, scratch_total = 0;                 // temporary buffer
+               flags_off = 0, sort_off = 0, pending_off = 0, scratch_total = 0;  // temporary buffer
+    uint32_t   pending_capacity = 0;
     SortLayout sort;
 };
 SceneLayout scene_layout(uint32_t instance_count);

@@ -21,15 +21,16 @@ namespace
 constexpr int      kRadixBits   = 8;
 constexpr int      kRadix       = 1 << kRadixBits;
 constexpr int      kPasses      = 4;
-constexpr int      kSortThreads = 512;
+constexpr int      kSortThreads = 256;                      // one thread per digit in the look-back
 constexpr int      kSortWarps   = kSortThreads / 32;
 constexpr int      kSortIpt     = 16;
-constexpr int      kSortTile    = kSortThreads * kSortIpt;  // 8192 pairs per tile
+constexpr int      kSortTile    = kSortThreads * kSortIpt;  // 4096 pairs per tile
 constexpr uint32_t kFlagAgg     = 1u << 30;                 // tile aggregate available
 constexpr uint32_t kFlagPrefix  = 2u << 30;                 // inclusive prefix available
 constexpr uint32_t kValueMask   = (1u << 30) - 1;
+constexpr int      kLookAhead   = 4;                        // predecessor tiles polled per look-back step
 
-constexpr size_t kSortSmemBytes = sizeof(uint32_t) * (kSortWarps * kRadix + kSortTile + 2 * kRadix + 16);
+constexpr size_t kSortSmemBytes = sizeof(uint32_t) * (kSortWarps * kRadix + 2 * kSortTile + 2 * kRadix + 16);
 
 __device__ __forceinline__ uint32_t lanemask_lt()
 {
@@ -37,18 +38,35 @@ __device__ __forceinline__ uint32_t lanemask_lt()
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
-__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p)
+// Look-back words are single-word messages (flag + count in one u32): relaxed gpu-scope accesses suffice.
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p)
 {
     uint32_t v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v)
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v)
 {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Exclusive scan of one value per thread over the first 256 threads (8 warps); all 512 threads call it.
+// Lanes of the warp holding the same 8-bit digit.  Eight ballots instead of MATCH.ANY: on sm_100 the match
+// instruction serialises over the distinct values in the warp and was 45 % of this kernel's stall samples
+// (profiles/round1_build.md); ballots are fixed cost.
+__device__ __forceinline__ uint32_t match_digit(uint32_t d)
+{
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < kRadixBits; ++b)
+    {
+        const bool     bit = (d >> b) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
+// Exclusive scan of one value per thread over the 256 threads of the CTA.
 __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_part /*>=8*/, int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
@@ -59,15 +77,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
         uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
-    if (warp < 8 && lane == 31) s_part[warp] = inc;
+    if (lane == 31) s_part[warp] = inc;
     __syncthreads();
     uint32_t add = 0;
-    if (warp < 8)
-    {
 #pragma unroll
-        for (int w = 0; w < 8; ++w)
-            if (w < warp) add += s_part[w];
-    }
+    for (int w = 0; w < kSortWarps; ++w)
+        if (w < warp) add += s_part[w];
     __syncthreads();
     return inc - v + add;
 }
@@ -92,21 +107,23 @@ __global__ void __launch_bounds__(256) k_sort_histogram(const uint32_t* __restri
 // One onesweep pass.  grid = number of tiles; tiles are claimed through an atomic ticket so that a
 // tile's predecessors are always resident or finished (forward progress of the look-back).
 template <bool kIdentityValues>
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 5)
     k_onesweep_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
                     uint32_t* __restrict__ vals_out, uint32_t n, int shift, const uint32_t* __restrict__ pass_hist,
                     uint32_t* __restrict__ ticket, uint32_t* __restrict__ status)
 {
     extern __shared__ uint32_t smem[];
-    uint32_t* s_warp_hist   = smem;                             // [kSortWarps][kRadix]
+    uint32_t* s_warp_hist   = smem;                               // [kSortWarps][kRadix]
     uint32_t* s_keys        = s_warp_hist + kSortWarps * kRadix;  // [kSortTile]
-    uint32_t* s_digit_base  = s_keys + kSortTile;               // [kRadix]
-    uint32_t* s_global_base = s_digit_base + kRadix;            // [kRadix]
-    uint32_t* s_misc        = s_global_base + kRadix;           // [16]
+    uint32_t* s_vals        = s_keys + kSortTile;                 // [kSortTile]
+    uint32_t* s_digit_base  = s_vals + kSortTile;                 // [kRadix]
+    uint32_t* s_global_base = s_digit_base + kRadix;              // [kRadix]
+    uint32_t* s_misc        = s_global_base + kRadix;             // [16]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_misc[8] = atomicAdd(ticket, 1u);
-    for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) s_warp_hist[i] = 0;
+#pragma unroll
+    for (int i = 0; i < kSortWarps; ++i) s_warp_hist[i * kRadix + tid] = 0;
     __syncthreads();
     const uint32_t tile  = s_misc[8];
     const uint32_t base  = tile * (uint32_t)kSortTile;
@@ -115,14 +132,22 @@ __global__ void __launch_bounds__(kSortThreads)
     // ---- load keys, warp-striped: item j of lane l in warp w is element w*512 + j*32 + l of the tile
     uint32_t       key[kSortIpt];
     const uint32_t woff = warp * (32 * kSortIpt) + lane;
-#pragma unroll
-    for (int j = 0; j < kSortIpt; ++j)
+    if (valid == (uint32_t)kSortTile)
     {
-        const uint32_t t = woff + j * 32;
-        key[j]           = (t < valid) ? keys_in[base + t] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < kSortIpt; ++j) key[j] = keys_in[base + woff + j * 32];
+    }
+    else
+    {
+#pragma unroll
+        for (int j = 0; j < kSortIpt; ++j)
+        {
+            const uint32_t t = woff + j * 32;
+            key[j]           = (t < valid) ? keys_in[base + t] : 0xFFFFFFFFu;
+        }
     }
 
-    // ---- rank inside the warp (stable: by item, then by lane) with match_any
+    // ---- rank inside the warp (stable: by item, then by lane)
     uint32_t  rank[kSortIpt];
     uint32_t* my_hist = s_warp_hist + warp * kRadix;
     const uint32_t lt = lanemask_lt();
@@ -130,7 +155,7 @@ __global__ void __launch_bounds__(kSortThreads)
     for (int j = 0; j < kSortIpt; ++j)
     {
         const uint32_t d      = (key[j] >> shift) & (kRadix - 1);
-        const uint32_t peers  = __match_any_sync(0xffffffffu, d);
+        const uint32_t peers  = match_digit(d);
         const int      leader = __ffs(peers) - 1;
         uint32_t       prev   = 0;
         if (lane == leader)
@@ -144,83 +169,76 @@ __global__ void __launch_bounds__(kSortThreads)
     }
     __syncthreads();
 
-    // ---- per-digit: exclusive scan over warps, tile totals, decoupled look-back
-    uint32_t tile_count = 0, padded_count = 0, excl = 0;
-    if (tid < kRadix)
+    // ---- per-digit (one thread each): exclusive scan over warps, tile totals, decoupled look-back
+    uint32_t padded_count = 0;
     {
         uint32_t acc = 0;
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w)
         {
-            const uint32_t c            = s_warp_hist[w * kRadix + tid];
+            const uint32_t c              = s_warp_hist[w * kRadix + tid];
             s_warp_hist[w * kRadix + tid] = acc;
             acc += c;
         }
         padded_count = acc;
-        tile_count   = (tid == kRadix - 1) ? acc - ((uint32_t)kSortTile - valid) : acc;  // padding keys are 0xFFFFFFFF
-        uint32_t* my_status = status + (size_t)tile * kRadix + tid;
-        if (tile == 0)
-            st_volatile(my_status, tile_count | kFlagPrefix);
-        else
-        {
-            st_volatile(my_status, tile_count | kFlagAgg);
-            int t = (int)tile - 1;
-            while (true)
-            {
-                const uint32_t s = ld_volatile(status + (size_t)t * kRadix + tid);
-                if ((s >> 30) == 0) continue;
-                excl += s & kValueMask;
-                if (s & kFlagPrefix) break;
-                --t;
-            }
-            st_volatile(my_status, ((excl + tile_count) & kValueMask) | kFlagPrefix);
-        }
     }
+    const uint32_t tile_count = (tid == kRadix - 1) ? padded_count - ((uint32_t)kSortTile - valid) : padded_count;  // padding keys are 0xFFFFFFFF
+    uint32_t*      my_status  = status + (size_t)tile * kRadix + tid;
+    st_status(my_status, tile_count | (tile == 0 ? kFlagPrefix : kFlagAgg));   // publish before anything else
     const uint32_t digit_base = block_exclusive_scan_256(padded_count, s_misc, tid);
-    const uint32_t hist_excl  = block_exclusive_scan_256(tid < kRadix ? pass_hist[tid] : 0u, s_misc, tid);
-    if (tid < kRadix)
+    const uint32_t hist_excl  = block_exclusive_scan_256(pass_hist[tid], s_misc, tid);
+    uint32_t excl = 0;
+    if (tile != 0)
     {
-        s_digit_base[tid]  = digit_base;
-        s_global_base[tid] = hist_excl + excl - digit_base;
+        int t = (int)tile - 1;
+        while (true)
+        {
+            uint32_t s[kLookAhead];
+#pragma unroll
+            for (int k = 0; k < kLookAhead; ++k) s[k] = (t - k >= 0) ? ld_status(status + (size_t)(t - k) * kRadix + tid) : kFlagPrefix;
+            int  k    = 0;
+            bool done = false;
+#pragma unroll
+            for (; k < kLookAhead; ++k)
+            {
+                if ((s[k] >> 30) == 0) break;
+                excl += s[k] & kValueMask;
+                if (s[k] & kFlagPrefix) { done = true; break; }
+            }
+            if (done) break;
+            t -= k;
+        }
+        st_status(my_status, ((excl + tile_count) & kValueMask) | kFlagPrefix);
     }
+    s_digit_base[tid]  = digit_base;
+    s_global_base[tid] = hist_excl + excl - digit_base;
     __syncthreads();
 
-    // ---- scatter keys into shared memory in digit order, then stream them out coalesced
-    uint32_t pos[kSortIpt];
+    // ---- scatter keys and values into shared memory in digit order, then stream them out coalesced
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j)
     {
-        const uint32_t d = (key[j] >> shift) & (kRadix - 1);
-        pos[j]           = s_digit_base[d] + my_hist[d] + rank[j];
-        s_keys[pos[j]]   = key[j];
+        const uint32_t d   = (key[j] >> shift) & (kRadix - 1);
+        const uint32_t pos = s_digit_base[d] + my_hist[d] + rank[j];
+        const uint32_t t   = woff + j * 32;
+        s_keys[pos]        = key[j];
+        uint32_t v         = 0;
+        if (kIdentityValues) v = base + t;
+        else if (t < valid) v = vals_in[base + t];
+        s_vals[pos] = v;
     }
     __syncthreads();
-    uint32_t gpos[kSortIpt];
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j)
     {
         const uint32_t p = tid + j * kSortThreads;
-        const uint32_t k = s_keys[p];
-        gpos[j]          = s_global_base[(k >> shift) & (kRadix - 1)] + p;
-        if (p < valid) keys_out[gpos[j]] = k;
-    }
-    __syncthreads();
-
-    // ---- values follow the same route
-#pragma unroll
-    for (int j = 0; j < kSortIpt; ++j)
-    {
-        const uint32_t t = woff + j * 32;
-        uint32_t       v = 0;
-        if (t < valid) v = kIdentityValues ? base + t : vals_in[base + t];
-        s_keys[pos[j]] = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kSortIpt; ++j)
-    {
-        const uint32_t p = tid + j * kSortThreads;
-        if (p < valid) vals_out[gpos[j]] = s_keys[p];
+        if (p < valid)
+        {
+            const uint32_t k = s_keys[p];
+            const uint32_t g = s_global_base[(k >> shift) & (kRadix - 1)] + p;
+            keys_out[g]      = k;
+            vals_out[g]      = s_vals[p];
+        }
     }
 }
 }  // namespace

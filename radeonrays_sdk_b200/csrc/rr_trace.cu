@@ -7,14 +7,20 @@
 // reference's, which is what makes ANY-hit ids and closest-hit ties reproducible.
 //
 // B200 mapping:
-//  * persistent CTAs (a multiple of the SM count); each warp strides over 32-ray chunks, so per-thread state
-//    -- and therefore the stack arena -- is bounded by resident threads, not by ray_count (the reference asks
-//    for 256 B of global stack per ray: 4 GiB for a 16 Mi batch, vlk/geometry_trace.cpp:169);
-//  * traversal stack: kSmemStack entries per thread in shared memory laid out [level][thread] (bank = lane,
-//    conflict free), deeper entries spill to the client's scratch buffer with the same layout (coalesced);
-//  * nodes are fetched as 4 x 16-byte read-only loads (ld.global.nc.v4) of the 64-byte aligned node.
-// Roofline: compulsory HBM traffic is 32 B/ray in + 16 B (or 4 B) out; the BVH is L2 resident, so the kernel
-// is bound by L1/L2 latency and issue rate, not HBM.
+//  * persistent CTAs (a multiple of the SM count); each warp pulls 32-ray chunks from a ticket, so per-thread state
+//    is bounded by resident threads, not by ray_count (the reference asks for 256 B of global stack per ray: 4 GiB
+//    for a 16 Mi batch, vlk/geometry_trace.cpp:169);
+//  * traversal stack: kSmemStack entries per thread in shared memory laid out [level][thread] (bank = lane, conflict
+//    free) and nothing else in the hot loop; a ray that would need more is appended to an overflow list and traced by
+//    a second, normally empty, launch (k_trace_deep) with a global-memory stack;
+//  * a node is fetched with two 32-byte read-only loads (LDG.E.256) of the 64-byte aligned node;
+//  * the two slab tests of a node visit use packed fma.rn.f32x2 (FFMA2) and, when the 32 rays of a chunk share a
+//    direction octant, a loop specialised for that octant in which min/max(far,near) per axis is a compile-time
+//    choice (bit-identical, see slab<>): 8 FMA-pipe + 8 min/max instructions instead of 12 + 20.
+// Roofline: compulsory HBM traffic is 32 B/ray in + 16 B (or 4 B) out and the BVH is L2 resident, so HBM is not the
+// bound.  Every lane pulls the 64 bytes of each node it visits through the SM's 128 B/clk L1 data path: 2 node visits
+// per clock per SM, i.e. ~8.7 Grays/s for Sponza primary rays (60.5 visits/ray) before any instruction is counted;
+// issue slots are the second limit (profiles/).
 #include <algorithm>
 #include <cstdlib>
 
@@ -26,8 +32,7 @@ namespace
 {
 constexpr int kTraceThreads = 128;
 constexpr int kSmemStack    = 32;   // entries per thread kept in shared memory
-constexpr int kSpillStack   = 96;   // further entries per thread in the scratch arena
-constexpr int kCtasPerSm    = 12;  // upper bound on resident CTAs per SM used for sizing the grid / spill arena
+constexpr int kDeepStack    = 192;  // entries per thread of the deep kernel's global-memory stack
 
 struct Vec3 { float x, y, z; };
 __device__ __forceinline__ Vec3 v3(float x, float y, float z) { Vec3 r{x, y, z}; return r; }
@@ -45,24 +50,76 @@ __device__ __forceinline__ float safe_inv(float d)
     return 1.0f / (fabsf(d) > e ? d : (d < 0.0f ? -e : e));
 }
 
+// ---- packed binary32 pairs: fma.rn.f32x2 (FFMA2 on sm_100) does two IEEE fused multiply-adds in one issue slot ----
+__device__ __forceinline__ uint64_t pack2(float a, float b)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// Read-only 32-byte half of a 64-byte node (LDG.E.256 on sm_100): two loads fetch a node.  volatile keeps both at the
+// top of the iteration (ptxas otherwise sinks the second below the leaf test, which puts another dependent-load
+// latency on every internal-node visit).
+__device__ __forceinline__ void ldg_half_node(const float4* p, float4& a, float4& b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 struct RayState
 {
-    Vec3  o, d, inv, oxinv;
+    Vec3     o, d, inv, oxinv;
+    uint64_t inv_xy, oxinv_xy;
     __device__ __forceinline__ void set(Vec3 oo, Vec3 dd)
     {
         o = oo; d = dd;
-        inv   = v3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
-        oxinv = v3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+        inv      = v3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+        oxinv    = v3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+        inv_xy   = pack2(inv.x, inv.y);
+        oxinv_xy = pack2(oxinv.x, oxinv.y);
+    }
+    // Octant of the direction (bit a set: axis a is traversed from max to min), or 8 when the specialised slab test
+    // must not be used: it is bit-identical to the generic one only while every plane distance is a number.
+    __device__ __forceinline__ int octant() const
+    {
+        const float big = 3.402823466e+38f;
+        const bool  ok  = fabsf(inv.x) <= big && fabsf(inv.y) <= big && fabsf(inv.z) <= big && fabsf(oxinv.x) <= big &&
+                        fabsf(oxinv.y) <= big && fabsf(oxinv.z) <= big;
+        return ok ? (int)((__float_as_uint(inv.x) >> 31) | ((__float_as_uint(inv.y) >> 31) << 1) | ((__float_as_uint(inv.z) >> 31) << 2)) : 8;
     }
 };
 
-// fast_intersect_aabb, common.h:150-164
+// fast_intersect_aabb, common.h:150-164.  kOct == 8: the shader's expression, min/max of both plane distances per axis.
+// kOct in 0..7 (all lanes of the warp share the direction octant): fma is monotone in the plane coordinate, so for
+// bmin <= bmax the larger of the two distances is known from the sign of inv alone and max(f,n) / min(f,n) -- 12 of the
+// 32 arithmetic instructions of a node visit -- reduce to a compile-time choice.  Same bits in t0/t1 either way.
+template <int kOct>
 __device__ __forceinline__ void slab(float4 bmin, float4 bmax, const RayState& r, float t_max, float t_min, float& t0, float& t1)
 {
-    const float fx = __fmaf_rn(bmax.x, r.inv.x, r.oxinv.x), fy = __fmaf_rn(bmax.y, r.inv.y, r.oxinv.y), fz = __fmaf_rn(bmax.z, r.inv.z, r.oxinv.z);
-    const float nx = __fmaf_rn(bmin.x, r.inv.x, r.oxinv.x), ny = __fmaf_rn(bmin.y, r.inv.y, r.oxinv.y), nz = __fmaf_rn(bmin.z, r.inv.z, r.oxinv.z);
-    const float ax = fmaxf(fx, nx), ay = fmaxf(fy, ny), az = fmaxf(fz, nz);
-    const float ix = fminf(fx, nx), iy = fminf(fy, ny), iz = fminf(fz, nz);
+    float lx, ly, hx, hy;
+    unpack2(fma2(pack2(bmin.x, bmin.y), r.inv_xy, r.oxinv_xy), lx, ly);
+    unpack2(fma2(pack2(bmax.x, bmax.y), r.inv_xy, r.oxinv_xy), hx, hy);
+    const float lz = __fmaf_rn(bmin.z, r.inv.z, r.oxinv.z), hz = __fmaf_rn(bmax.z, r.inv.z, r.oxinv.z);
+    float ax, ay, az, ix, iy, iz;
+    if (kOct == 8)
+    {
+        ax = fmaxf(hx, lx); ay = fmaxf(hy, ly); az = fmaxf(hz, lz);
+        ix = fminf(hx, lx); iy = fminf(hy, ly); iz = fminf(hz, lz);
+    }
+    else
+    {
+        ax = (kOct & 1) ? lx : hx; ix = (kOct & 1) ? hx : lx;
+        ay = (kOct & 2) ? ly : hy; iy = (kOct & 2) ? hy : ly;
+        az = (kOct & 4) ? lz : hz; iz = (kOct & 4) ? hz : lz;
+    }
     t1 = fminf(fminf(az, fminf(ax, ay)), t_max);
     t0 = fmaxf(fmaxf(iz, fmaxf(ix, iy)), t_min);
 }
@@ -105,24 +162,37 @@ __device__ __forceinline__ void transform_ray(const InstanceRecord* rec, Vec3 o,
     od = v3(dot(v3(m0), d), dot(v3(m1), d), dot(v3(m2), d));
 }
 
-struct Stack
+// Traversal stack of the main kernel: kSmemStack entries per thread in shared memory, laid out [level][thread]
+// (bank = lane, conflict free).  push() refuses the entry that does not fit; the ray is then handed to the deep kernel.
+struct SmemStack
 {
-    uint32_t* smem;    // &s_stack[tid]
-    uint32_t* spill;   // &arena[slot]
-    uint32_t  spill_stride;
+    uint32_t* base;  // &s_stack[tid]
     int       sp;
-    __device__ __forceinline__ void push(uint32_t v)
+    __device__ __forceinline__ bool push(uint32_t v)
     {
-        if (sp < kSmemStack) smem[sp * kTraceThreads] = v;
-        else if (sp < kSmemStack + kSpillStack) spill[(size_t)(sp - kSmemStack) * spill_stride] = v;
-        else return;  // deeper than any tree this builder can produce; drop rather than corrupt
+        if (sp >= kSmemStack) return false;
+        base[sp * kTraceThreads] = v;
         ++sp;
+        return true;
     }
-    __device__ __forceinline__ uint32_t pop()
+    __device__ __forceinline__ uint32_t pop() { --sp; return base[sp * kTraceThreads]; }
+};
+// Stack of the deep kernel: kDeepStack entries per thread in the scratch arena, same [level][thread] layout (coalesced,
+// L1/L2 resident).  A radix tree over distinct (30-bit code, 32-bit index) keys is at most 62 levels deep and treelet
+// restructuring only permutes 7-leaf treelets, so kDeepStack = 192 covers TLAS + sentinel + BLAS with margin; a deeper
+// entry would be dropped rather than corrupt memory.
+struct DeepStack
+{
+    uint32_t* base;  // &arena[thread slot]
+    uint32_t  stride;
+    int       sp;
+    __device__ __forceinline__ bool push(uint32_t v)
     {
-        --sp;
-        return sp < kSmemStack ? smem[sp * kTraceThreads] : spill[(size_t)(sp - kSmemStack) * spill_stride];
+        if (sp < kDeepStack) base[(size_t)sp * stride] = v;
+        ++sp;
+        return true;
     }
+    __device__ __forceinline__ uint32_t pop() { --sp; return sp < kDeepStack ? base[(size_t)sp * stride] : kInvalid; }
 };
 
 struct TraceParams
@@ -133,9 +203,13 @@ struct TraceParams
     uint32_t              ray_count;
     const uint32_t*       indirect;
     void*                 hits;
-    uint32_t*             arena;
-    uint32_t*             ticket;   // chunk counter, first word of the scratch buffer
+    uint32_t*             arena;          // deep-kernel stacks
+    uint32_t*             ticket;         // scratch header word 0: chunk counter of the main kernel
+    uint32_t*             overflow_count; // word 1: rays whose stack did not fit in shared memory
+    uint32_t*             deep_ticket;    // word 2: chunk counter of the deep kernel
+    uint32_t*             overflow_list;  // [ray_count] indices of those rays
     int                   first_found;
+    int                   force_generic;
 };
 
 // Leaving an instance: restore the world-space ray (isect_2l.comp:279-287) and pop again.
@@ -157,42 +231,35 @@ struct TraceParams
 // an instance, or tests the triangle.  Measured alternatives that were NOT kept (profiles/round1_trace_modes.md):
 // a while-while restructuring (descend until a leaf, then test) was 25-40 % slower on B200, and per-lane ray refill
 // (persistent threads with batched replacement) 20-60 % slower, on coherent and incoherent rays alike.
-template <bool kAny, bool kFullHit, bool kTwoLevel>
-__device__ __forceinline__ void trace_ray(const TraceParams& P, Stack& st, uint32_t gidx)
+template <bool kAny, bool kFullHit, bool kTwoLevel, int kOct, class StackT>
+__device__ __forceinline__ void trace_ray(const TraceParams& P, StackT& st, uint32_t gidx, bool valid, float4 r0, float4 r1, RayState& ray)
 {
-    const float4 r0 = __ldg(P.rays + 2 * (size_t)gidx), r1 = __ldg(P.rays + 2 * (size_t)gidx + 1);
-    const float  min_t = r0.w;
-    RayState ray;
-    ray.set(v3(r0), v3(r1));
-    float    closest      = r1.w;
-    uint32_t closest_addr = kInvalid, closest_prim = kInvalid, closest_inst = kInvalid;
-    uint32_t cur_inst     = kInvalid;
-    const Node* cur_bvh   = P.bvh;
+    const float min_t        = r0.w;
+    float       closest      = r1.w;
+    uint32_t    closest_addr = kInvalid, closest_prim = kInvalid, closest_inst = kInvalid;
+    uint32_t    cur_inst     = kInvalid;
+    const Node* cur_bvh      = P.bvh;
     st.sp = 0;
     st.push(kInvalid);
-    uint32_t addr = 0;
+    uint32_t addr = valid ? 0u : kInvalid;
     while (addr != kInvalid)
     {
         const float4* np = reinterpret_cast<const float4*>(cur_bvh + addr);
-        // all four quads are requested at once: the fourth is dead for leaves, but issuing it after the
-        // leaf/internal branch would put a second dependent load on every internal-node visit
-        const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+        float4 q0, q1, q2, q3;
+        ldg_half_node(np, q0, q1);
+        ldg_half_node(np + 2, q2, q3);
         if (wbits(q0) != kInvalid)
         {
             float a0, a1, b0, b1;
-            slab(q0, q1, ray, closest, min_t, a0, a1);
-            slab(q2, q3, ray, closest, min_t, b0, b1);
+            slab<kOct>(q0, q1, ray, closest, min_t, a0, a1);
+            slab<kOct>(q2, q3, ray, closest, min_t, b0, b1);
             const bool t0 = a0 <= a1, t1 = b0 <= b1;
-            if (t0 || t1)
-            {
-                const bool c1first = t1 && (a0 > b0);
-                const uint32_t c0 = wbits(q0), c1 = wbits(q1);
-                uint32_t deferred;
-                if (c1first || !t0) { addr = c1; deferred = c0; }
-                else { addr = c0; deferred = c1; }
-                if (t0 && t1) st.push(deferred);
-                continue;
-            }
+            const bool c1first = t1 && (a0 > b0);
+            const bool take1   = c1first || !t0;
+            const uint32_t c0 = wbits(q0), c1 = wbits(q1);
+            const uint32_t near_child = take1 ? c1 : c0, far_child = take1 ? c0 : c1;
+            if (t0 && t1 && !st.push(far_child)) goto overflow;
+            if (t0 || t1) { addr = near_child; continue; }
         }
         else if (kTwoLevel && cur_inst == kInvalid)
         {   // top-level leaf: enter the instance (isect_2l.comp:231-245)
@@ -202,7 +269,7 @@ __device__ __forceinline__ void trace_ray(const TraceParams& P, Stack& st, uint3
             transform_ray(rec, ray.o, ray.d, oo, od);
             ray.set(oo, od);
             cur_bvh = rec->blas;
-            st.push(kSentinel);
+            if (!st.push(kSentinel)) goto overflow;
             addr = 0;
             continue;
         }
@@ -239,6 +306,7 @@ __device__ __forceinline__ void trace_ray(const TraceParams& P, Stack& st, uint3
         }
         RR_POP_NEXT();
     }
+    if (!valid) return;
     if (closest_addr != kInvalid)
     {
         if (kFullHit)
@@ -265,12 +333,19 @@ __device__ __forceinline__ void trace_ray(const TraceParams& P, Stack& st, uint3
         if (kFullHit) reinterpret_cast<uint32_t*>(P.hits)[4 * (size_t)gidx + 2] = kInvalid;
         else reinterpret_cast<uint32_t*>(P.hits)[gidx] = kInvalid;
     }
+    return;
+overflow:
+    // nothing has been written for this ray yet: the deep kernel traces it again from the start
+    P.overflow_list[atomicAdd(P.overflow_count, 1u)] = gidx;
 }
 #undef RR_POP_NEXT
 
 // Persistent warps pull one 32-ray chunk at a time from a global ticket (P.ticket, zeroed by a memset node before
 // the launch) and trace it to completion.  Against a static warp-stride assignment this removes the end-of-kernel
 // imbalance: +29 % on coherent primary rays, +39 % on shadow rays (profiles/round1_trace_modes.md).
+// One-level kernels dispatch each chunk to the loop specialised for its direction octant when all 32 rays agree
+// (coherent batches almost always do); mixed chunks, and every two-level trace (the ray changes octant per instance),
+// run the generic loop.
 template <bool kAny, bool kFullHit, bool kTwoLevel>
 __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(TraceParams P)
 {
@@ -278,18 +353,65 @@ __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(Tra
     uint32_t count = P.ray_count;
     if (P.indirect) count = min(count, __ldg(P.indirect));  // isect.comp:98-103
     const uint32_t lane = threadIdx.x & 31;
-    Stack st;
-    st.smem         = s_stack + threadIdx.x;
-    st.spill        = P.arena + (blockIdx.x * kTraceThreads + threadIdx.x);
-    st.spill_stride = gridDim.x * kTraceThreads;
+    SmemStack st;
+    st.base = s_stack + threadIdx.x;
     while (true)
     {
         uint32_t chunk = 0;
         if (lane == 0) chunk = atomicAdd(P.ticket, 1u);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if ((uint64_t)chunk * 32 >= count) break;
-        const uint32_t gidx = chunk * 32 + lane;
-        if (gidx < count) trace_ray<kAny, kFullHit, kTwoLevel>(P, st, gidx);
+        const uint32_t gidx  = chunk * 32 + lane;
+        const bool     valid = gidx < count;
+        const uint32_t ridx  = valid ? gidx : count - 1;  // tail lanes shadow the last ray and write nothing
+        const float4 r0 = __ldg(P.rays + 2 * (size_t)ridx), r1 = __ldg(P.rays + 2 * (size_t)ridx + 1);
+        RayState ray;
+        ray.set(v3(r0), v3(r1));
+        int oct = 8;
+        if (!kTwoLevel && !P.force_generic)
+        {
+            oct = ray.octant();
+            if (!__all_sync(0xffffffffu, oct == __shfl_sync(0xffffffffu, oct, 0))) oct = 8;
+        }
+        switch (oct)
+        {
+        case 0: trace_ray<kAny, kFullHit, kTwoLevel, 0>(P, st, gidx, valid, r0, r1, ray); break;
+        case 1: trace_ray<kAny, kFullHit, kTwoLevel, 1>(P, st, gidx, valid, r0, r1, ray); break;
+        case 2: trace_ray<kAny, kFullHit, kTwoLevel, 2>(P, st, gidx, valid, r0, r1, ray); break;
+        case 3: trace_ray<kAny, kFullHit, kTwoLevel, 3>(P, st, gidx, valid, r0, r1, ray); break;
+        case 4: trace_ray<kAny, kFullHit, kTwoLevel, 4>(P, st, gidx, valid, r0, r1, ray); break;
+        case 5: trace_ray<kAny, kFullHit, kTwoLevel, 5>(P, st, gidx, valid, r0, r1, ray); break;
+        case 6: trace_ray<kAny, kFullHit, kTwoLevel, 6>(P, st, gidx, valid, r0, r1, ray); break;
+        case 7: trace_ray<kAny, kFullHit, kTwoLevel, 7>(P, st, gidx, valid, r0, r1, ray); break;
+        default: trace_ray<kAny, kFullHit, kTwoLevel, 8>(P, st, gidx, valid, r0, r1, ray); break;
+        }
+    }
+}
+
+// Second launch of every intersect: traces the (normally zero) rays whose deferred-node stack outgrew shared memory,
+// with the generic loop and a global-memory stack.  Exits at once when the list is empty.
+template <bool kAny, bool kFullHit, bool kTwoLevel>
+__global__ void __launch_bounds__(kTraceThreads) k_trace_deep(TraceParams P)
+{
+    const uint32_t count = *P.overflow_count;
+    if (count == 0) return;
+    const uint32_t lane = threadIdx.x & 31;
+    DeepStack st;
+    st.base   = P.arena + (blockIdx.x * kTraceThreads + threadIdx.x);
+    st.stride = gridDim.x * kTraceThreads;
+    while (true)
+    {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(P.deep_ticket, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if ((uint64_t)chunk * 32 >= count) break;
+        const uint32_t i     = chunk * 32 + lane;
+        const bool     valid = i < count;
+        const uint32_t gidx  = P.overflow_list[valid ? i : count - 1];
+        const float4 r0 = __ldg(P.rays + 2 * (size_t)gidx), r1 = __ldg(P.rays + 2 * (size_t)gidx + 1);
+        RayState ray;
+        ray.set(v3(r0), v3(r1));
+        trace_ray<kAny, kFullHit, kTwoLevel, 8>(P, st, gidx, valid, r0, r1, ray);
     }
 }
 
@@ -299,7 +421,7 @@ inline int ctas_per_sm(bool two_level)
 {
     static int env = [] { const char* e = std::getenv("RR_CUDA_TRACE_CTAS_PER_SM"); return e ? std::atoi(e) : 0; }();
     const int v = env > 0 ? env : (two_level ? 8 : 10);
-    return std::min(v, kCtasPerSm);
+    return std::min(v, 16);
 }
 inline int trace_grid(const DeviceInfo& dev, uint32_t ray_count, int per_sm)
 {
@@ -307,19 +429,24 @@ inline int trace_grid(const DeviceInfo& dev, uint32_t ray_count, int per_sm)
     return (int)std::max<size_t>(1, std::min<size_t>(need, (size_t)dev.sm_count * per_sm));
 }
 
+constexpr int kDeepCtasPerSm = 2;
+
 template <bool kAny, bool kFullHit, bool kTwoLevel>
 void launch(const DeviceInfo& dev, cudaStream_t s, const TraceParams& P)
 {
     k_trace<kAny, kFullHit, kTwoLevel><<<trace_grid(dev, P.ray_count, ctas_per_sm(kTwoLevel)), kTraceThreads, 0, s>>>(P);
+    k_trace_deep<kAny, kFullHit, kTwoLevel><<<trace_grid(dev, P.ray_count, kDeepCtasPerSm), kTraceThreads, 0, s>>>(P);
 }
 }  // namespace
 
-// Scratch: [256 B header holding the chunk ticket | spill arena: kSpillStack words for every resident thread slot]
-// (never more slots than rays).
+// Scratch: [256 B header: main ticket, overflow count, deep ticket | overflow list: 4 B per ray | deep-kernel stacks:
+// kDeepStack words for each of its thread slots].  The reference asks for 256 B per ray (vlk/geometry_trace.cpp:169).
 constexpr size_t kScratchHeader = 256;
+static size_t overflow_list_bytes(uint32_t ray_count) { return align_up(sizeof(uint32_t) * (size_t)ray_count, 256); }
 size_t trace_scratch_size(const DeviceInfo& dev, uint32_t ray_count)
 {
-    return kScratchHeader + (size_t)trace_grid(dev, ray_count, kCtasPerSm) * kTraceThreads * kSpillStack * sizeof(uint32_t);
+    return kScratchHeader + overflow_list_bytes(ray_count) +
+           (size_t)trace_grid(dev, ray_count, kDeepCtasPerSm) * kTraceThreads * kDeepStack * sizeof(uint32_t);
 }
 
 void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
@@ -328,8 +455,13 @@ void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
     if (a.scratch_bytes < trace_scratch_size(dev, a.ray_count)) throw std::runtime_error("trace scratch buffer too small");
     TraceParams P;
     P.bvh = a.bvh; P.instances = a.instances; P.rays = reinterpret_cast<const float4*>(a.rays); P.ray_count = a.ray_count;
-    P.indirect = a.indirect_count; P.hits = a.hits; P.ticket = a.scratch; P.arena = a.scratch + kScratchHeader / sizeof(uint32_t); P.first_found = a.first_found_tie_rule ? 1 : 0;
-    RR_CUDA_CHECK(cudaMemsetAsync(a.scratch, 0, sizeof(uint32_t), s));
+    P.indirect = a.indirect_count; P.hits = a.hits; P.first_found = a.first_found_tie_rule ? 1 : 0;
+    P.ticket = a.scratch; P.overflow_count = a.scratch + 1; P.deep_ticket = a.scratch + 2;
+    P.overflow_list = a.scratch + kScratchHeader / sizeof(uint32_t);
+    P.arena = P.overflow_list + overflow_list_bytes(a.ray_count) / sizeof(uint32_t);
+    static const int force_generic = [] { const char* e = std::getenv("RR_CUDA_TRACE_GENERIC"); return e ? std::atoi(e) : 0; }();
+    P.force_generic = force_generic;
+    RR_CUDA_CHECK(cudaMemsetAsync(a.scratch, 0, 4 * sizeof(uint32_t), s));
     const bool any = a.query == RR_INTERSECT_QUERY_ANY, full = a.output == RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, two = a.instances != nullptr;
     if (!two)
     {
@@ -341,7 +473,7 @@ void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
         if (any) { if (full) launch<true, true, true>(dev, s, P); else launch<true, false, true>(dev, s, P); }
         else     { if (full) launch<false, true, true>(dev, s, P); else launch<false, false, true>(dev, s, P); }
     }
-    ++*dev.launches;
+    *dev.launches += 2;
     RR_CUDA_CHECK(cudaGetLastError());
 }
 

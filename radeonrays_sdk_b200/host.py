@@ -155,3 +155,64 @@ class Scene:
 
 class RayBuffers:
     pass
+
+
+class HostTracePipeline:
+    """rrCmdIntersect over a batch whose rays and hits live in HOST (pinned) memory.
+
+    The batch is cut into `chunks` contiguous slices (multiples of 32 rays, sharding.shard_range); slice c is copied
+    host->device on a copy stream, traced by its own pre-recorded command stream on the context's stream, and its hits
+    are copied device->host on a third stream, so the PCIe transfers in both directions overlap each other and the
+    kernel.  run() returns with the context stream waiting on the last device->host copy: an event recorded on it
+    afterwards (or rrSumbitCommandStream's event of a later submit) covers the whole batch.
+    """
+
+    def __init__(self, engine, target, ray_count, query=api.RR_INTERSECT_QUERY_CLOSEST, output=api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT,
+                 chunks=8):
+        from .sharding import shard_range
+        self.engine, self.ctx, self.n = engine, engine.ctx, int(ray_count)
+        self.hit_size = 16 if output == api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT else 4
+        self.buffers = engine.make_ray_buffers(ray_count, output)
+        self.copy_in, self.copy_out = torch.cuda.Stream(engine.device), torch.cuda.Stream(engine.device)
+        self.spans, self.streams, self.ev_in, self.ev_done, self.ev_out = [], [], [], [], []
+        b = self.buffers
+        for c in range(chunks):
+            lo, hi = shard_range(self.n, c, chunks)
+            if hi <= lo:
+                continue
+            cs = self.ctx.allocate_command_stream()
+            p_rays = self.ctx.tensor_ptr(b.d_rays, 32 * lo)
+            p_hits = self.ctx.tensor_ptr(b.d_hits, self.hit_size * lo)
+            self.ctx.cmd_intersect(target.p_nodes, query, p_rays, hi - lo, None, output, p_hits, b.p_scratch, cs)
+            self.spans.append((lo, hi))
+            self.streams.append(cs)
+            self.ev_in.append(torch.cuda.Event())
+            self.ev_done.append(torch.cuda.Event())
+            self.ev_out.append(torch.cuda.Event())
+        self.first = True
+
+    def run(self, h_rays, h_hits):
+        """h_rays: pinned uint8 tensor [32*n]; h_hits: pinned uint8 tensor [hit_size*n]."""
+        b, compute = self.buffers, self.engine.torch_stream
+        for c, (lo, hi) in enumerate(self.spans):
+            if not self.first:
+                self.copy_in.wait_event(self.ev_done[c])      # the previous batch's trace has consumed this ray slice
+                compute.wait_event(self.ev_out[c])            # ... and its hits have left the device
+            with torch.cuda.stream(self.copy_in):
+                b.d_rays[32 * lo: 32 * hi].copy_(h_rays[32 * lo: 32 * hi], non_blocking=True)
+                self.ev_in[c].record(self.copy_in)
+            compute.wait_event(self.ev_in[c])
+            self.ctx.release_event(self.ctx.submit(self.streams[c]))
+            self.ev_done[c].record(compute)
+            self.copy_out.wait_event(self.ev_done[c])
+            with torch.cuda.stream(self.copy_out):
+                h_hits[self.hit_size * lo: self.hit_size * hi].copy_(b.d_hits[self.hit_size * lo: self.hit_size * hi], non_blocking=True)
+                self.ev_out[c].record(self.copy_out)
+        compute.wait_stream(self.copy_out)
+        self.first = False
+
+    def close(self):
+        torch.cuda.synchronize(self.engine.device)
+        for cs in self.streams:
+            self.ctx.release_command_stream(cs)
+        self.streams = []
