@@ -23,6 +23,7 @@ typedef struct
     size_t morton_codes_offset;
     size_t sorted_codes_offset;
     size_t sorted_refs_offset;
+    size_t sort_tmp_values_offset; /* ping-pong value buffer of the sort, dead once the sort has finished */
 } RRCudaBuildScratchLayout;
 RR_API RRError rrCudaDebugGetBuildScratchLayout(RRContext context, uint32_t triangle_count, RRCudaBuildScratchLayout* layout);
 

@@ -61,7 +61,7 @@ class RRMemoryRequirements(C.Structure):
 
 class RRCudaBuildScratchLayout(C.Structure):
     _fields_ = [("scene_aabb_offset", C.c_size_t), ("morton_codes_offset", C.c_size_t),
-                ("sorted_codes_offset", C.c_size_t), ("sorted_refs_offset", C.c_size_t)]
+                ("sorted_codes_offset", C.c_size_t), ("sorted_refs_offset", C.c_size_t), ("sort_tmp_values_offset", C.c_size_t)]
 
 
 class RRCudaSceneLayout(C.Structure):

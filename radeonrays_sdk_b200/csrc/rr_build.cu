@@ -189,6 +189,7 @@ struct EmitParams
     uint32_t*       pending_count;     // preset to 0: climbers handed from the local to the global kernel
     uint2*          pending;           // [pending_capacity] (split position, far bound) of each
     uint32_t        pending_capacity;
+    unsigned long long* timeline;      // debug (RR_EMIT_TIMELINE builds): 8 timestamps per sampled CTA
     // mesh leaves
     MeshDesc mesh;
     // scene leaves
@@ -240,32 +241,30 @@ __device__ __forceinline__ void affine_inverse(const float* m, float4& r0, float
 // parent's split position) and at the LEFT end if it is a right child (split+1); the root is 0; leaf j is node N-1+j.
 //
 // B200 mapping (two kernels):
-//   k_emit_fit   -- a CTA owns a window of kEmitLeaves consecutive sorted leaves, staged in shared memory.  Every
-//     subtree that lies inside the window also has its internal node indices inside the window, so:
-//       T) thread t determines the range and split of internal node b0+t exactly like the reference's emit kernel
-//          (FindSpan / FindSplit as two binary descents over delta(i,j), shared-memory codes, no divergence); a range
-//          that reaches a leaf outside the window marks the node as "not local";
-//       B) boxes of the local nodes are fitted in rounds (a node fires once both children are ready; leaves are ready
-//          at once): pure min/max, no atomics, no fences, as many rounds as the window's subtrees are deep;
-//       F) finished nodes leave as fully coalesced 16-byte quads (4 lanes per 64-byte node);
-//       H) local roots -- nodes and leaves whose parent is not local, ~2 log2(window) per CTA -- are handed to
-//          k_emit_global as (split position, far bound) pairs.
-//   k_emit_global -- one thread per handed-over node climbs with the classic rendezvous on global words (first arrival
-//     leaves its far bound and retires, second emits the parent), reading sibling boxes back with ld.cg.
-// Keeping the climbs out of k_emit_fit matters: a CTA that waited for its one climber to reach the root held 512 thread
-// slots for ~50 us and the kernel ran 4x slower than its traffic allows (profiles/round1_summary.md).
-constexpr int kEmitLeaves = 512;  // leaves (= threads) per CTA
+//   k_emit_fit   -- a CTA owns a window of kEmitLeaves consecutive sorted leaves.  Every subtree that lies inside the
+//     window also has its internal node indices inside the window, so the classic bottom-up construction runs entirely
+//     on shared memory: one climber per leaf owns a range [l,r] and the node covering it; the range is a left child iff
+//     delta(r,r+1) > delta(l-1,l); both children meet at the rendezvous word of their split position -- the first to
+//     arrive leaves its far bound and retires, the second learns the sibling's bound, hence the parent's range and its
+//     Karras index, writes the parent's finished 64-byte image into shared memory and climbs on.  The images leave as
+//     fully coalesced 16-byte quads (each node byte is written to HBM exactly once); climbers whose sibling lies outside
+//     the window (~2 log2(window) per CTA) are handed to k_emit_global as (split position, far bound) pairs.
+//   k_emit_global -- one thread per handed-over climber continues the same protocol on global rendezvous words,
+//     reading sibling boxes back with ld.cg.
+// Keeping the long climbs out of k_emit_fit matters: a CTA that waited for its one climber to reach the root held its
+// thread slots for ~50 us and the single-kernel version ran 7 ms for 50 M triangles (profiles/round1_summary.md lists
+// the variants that were measured: barrier-paced rounds, flag polling, a one-warp tail, 256-leaf windows).
+constexpr int      kEmitLeaves = 512;  // leaves (= threads) per CTA
+constexpr uint32_t kDone       = 0xFFFFFFFEu;
 
 struct EmitSmem
 {
-    float4   box[2 * kEmitLeaves][2];  // (lo, hi) of internal node b0+i at [i], of leaf b0+j at [kEmitLeaves + j]
-    float    leaf[kEmitLeaves][9];     // mesh: v0 v1 v2 of the leaf's triangle
-    uint32_t codes[kEmitLeaves + 2];   // sorted codes of leaves b0-1 .. b1+1
-    uint32_t leaf_ref[kEmitLeaves];
-    uint32_t leaf_parent[kEmitLeaves];
-    uint32_t ic0[kEmitLeaves], ic1[kEmitLeaves], iparent[kEmitLeaves];  // ic0 == INVALID: node not local
-    uint32_t ifar[kEmitLeaves];        // the other end of local node i's range
-    uint8_t  ready[kEmitLeaves];
+    // node images, quad-major (quad k of node i at [k][i], one pad entry per row): a thread touching "its" node is
+    // bank-conflict free and the flush is a plain copy
+    float4   iq[4][kEmitLeaves + 1];   // internal nodes b0 .. b0+511; [0][i].w == INVALID: not formed in this window
+    float4   lq[4][kEmitLeaves + 1];   // leaves b0 .. b0+511
+    uint32_t flag[kEmitLeaves + 2];    // rendezvous per local split; [kEmitLeaves] / [+1]: climber stopped at the left / right window edge
+    uint8_t  delta[kEmitLeaves + 2];   // delta(a, a+1) for a = b0-1 .. b1
 };
 
 // The rendezvous protocol on the global words, for a node that is already in memory.  (split, far) identify it: the
@@ -319,36 +318,73 @@ __device__ void global_climb(const EmitParams& p, uint32_t split, uint32_t far)
     }
 }
 
+// Box of a node from its shared-memory image.
+template <bool kScene>
+__device__ __forceinline__ void image_box(const EmitSmem& S, uint32_t node, int leaf0, int b0, float3& lo, float3& hi)
+{
+    if (node >= (uint32_t)leaf0)
+    {
+        const int k = (int)node - leaf0 - b0;
+        const float4 q0 = S.lq[0][k], q1 = S.lq[1][k];
+        if (kScene) { lo = xyz(q0); hi = xyz(q1); }
+        else
+        {
+            const float4 q2 = S.lq[2][k];
+            lo = min3(min3(xyz(q0), xyz(q1)), xyz(q2));
+            hi = max3(max3(xyz(q0), xyz(q1)), xyz(q2));
+        }
+    }
+    else
+    {
+        const int k = (int)node - b0;
+        lo = min3(xyz(S.iq[0][k]), xyz(S.iq[2][k]));
+        hi = max3(xyz(S.iq[1][k]), xyz(S.iq[3][k]));
+    }
+}
+
 template <bool kScene>
 __global__ void __launch_bounds__(kEmitLeaves, 3) k_emit_fit(EmitParams p)
 {
     extern __shared__ __align__(16) unsigned char emit_smem_raw[];
     EmitSmem& S = *reinterpret_cast<EmitSmem*>(emit_smem_raw);
     __shared__ uint32_t s_pending_n, s_pending_base;
-    const int      n = (int)p.n, leaf0 = n - 1;
-    const int      tid = threadIdx.x;
-    const int      b0  = blockIdx.x * kEmitLeaves;
-    const int      cnt = min(kEmitLeaves, n - b0);
-    const int      b1  = b0 + cnt - 1;
-    const bool     valid = tid < cnt;
+    const int  n = (int)p.n, leaf0 = n - 1;
+    const int  tid = threadIdx.x;
+    const int  b0  = blockIdx.x * kEmitLeaves;
+    const int  cnt = min(kEmitLeaves, n - b0);
+    const int  b1  = b0 + cnt - 1;
+    const bool valid = tid < cnt;
+    const int  j = b0 + tid;  // this thread's leaf
+    // phase timeline of every 64th CTA (tools/emit_timeline.py), compiled in with -DRR_EMIT_TIMELINE
+#ifdef RR_EMIT_TIMELINE
+#define RR_EMIT_STAMP(k) do { if (p.timeline && tid == 0 && (blockIdx.x & 63) == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.timeline[(blockIdx.x >> 6) * 8 + (k)] = t_; } } while (0)
+#else
+#define RR_EMIT_STAMP(k) do { } while (0)
+#endif
+    RR_EMIT_STAMP(0);
 
-    for (int i = tid; i < cnt + 2; i += kEmitLeaves)
+    // delta(a, a+1), a = b0-1+k (lbvh_emit_hierarchy_mesh.comp:85-103 up to a monotone map: true clz); fits a byte
+    for (int k = tid; k < cnt + 1; k += kEmitLeaves)
     {
-        const int gi = b0 + i;  // leaf index + 1
-        S.codes[i]   = (gi >= 1 && gi <= n) ? p.codes[gi - 1] : 0u;
+        const int a = b0 - 1 + k;
+        uint32_t  d = 0;
+        if (a >= 0 && a + 1 < n)
+        {
+            const uint32_t x = p.codes[a] ^ p.codes[a + 1];
+            d = x ? __clz(x) : 32 + __clz((uint32_t)(a ^ (a + 1)));
+        }
+        S.delta[k] = (uint8_t)d;
     }
     if (tid == 0) s_pending_n = 0;
-    S.ic0[tid]         = kInvalid;
-    S.iparent[tid]     = kInvalid;
-    S.leaf_parent[tid] = kInvalid;
-    S.ready[tid]       = 0;
+    S.flag[tid] = kInvalid;
+    if (tid < 2) S.flag[kEmitLeaves + tid] = kInvalid;
+    reinterpret_cast<uint32_t*>(&S.iq[0][tid])[3] = kInvalid;  // not formed (yet)
 
-    // ---- leaves: gather, keep for the flush, publish their boxes ---------------------------------------------------
+    // ---- leaves: gather, build the leaf image, keep the box in registers ------------------------------------------
+    float3 lo = make_float3(0.f, 0.f, 0.f), hi = lo;
     if (valid)
     {
-        const uint32_t ref = p.refs[b0 + tid];
-        S.leaf_ref[tid]    = ref;
-        float3 lo, hi;
+        const uint32_t ref = p.refs[j];
         if (kScene)
         {   // lbvh_fit_aabb_scene.comp:113-130
             const float4 bmin = p.boxes[2 * (size_t)ref], bmax = p.boxes[2 * (size_t)ref + 1];
@@ -363,6 +399,10 @@ __global__ void __launch_bounds__(kEmitLeaves, 3) k_emit_fit(EmitParams p)
             p.fwd[3 * (size_t)ref + 0] = make_float4(d.m[0], d.m[1], d.m[2], d.m[3]);
             p.fwd[3 * (size_t)ref + 1] = make_float4(d.m[4], d.m[5], d.m[6], d.m[7]);
             p.fwd[3 * (size_t)ref + 2] = make_float4(d.m[8], d.m[9], d.m[10], d.m[11]);
+            S.lq[0][tid] = pack(lo, kInvalid);
+            S.lq[1][tid] = pack(hi, ref);
+            S.lq[2][tid] = pack(lo, kInvalid);
+            S.lq[3][tid] = pack(hi, 0u);
         }
         else
         {   // lbvh_fit_aabb_mesh.comp:139-163
@@ -371,129 +411,90 @@ __global__ void __launch_bounds__(kEmitLeaves, 3) k_emit_fit(EmitParams p)
             const float3 v0 = ld3(p.mesh.vertices + (size_t)i0 * p.mesh.stride_floats);
             const float3 v1 = ld3(p.mesh.vertices + (size_t)i1 * p.mesh.stride_floats);
             const float3 v2 = ld3(p.mesh.vertices + (size_t)i2 * p.mesh.stride_floats);
-            float* v = S.leaf[tid];
-            v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v1.x; v[4] = v1.y; v[5] = v1.z; v[6] = v2.x; v[7] = v2.y; v[8] = v2.z;
             lo = min3(min3(v0, v1), v2);
             hi = max3(max3(v0, v1), v2);
+            S.lq[0][tid] = pack(v0, kInvalid);
+            S.lq[1][tid] = pack(v1, ref);
+            S.lq[2][tid] = pack(v2, kInvalid);
+            S.lq[3][tid] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        S.box[kEmitLeaves + tid][0] = make_float4(lo.x, lo.y, lo.z, 0.f);
-        S.box[kEmitLeaves + tid][1] = make_float4(hi.x, hi.y, hi.z, 0.f);
     }
     __syncthreads();
+    RR_EMIT_STAMP(1);
 
-    // delta(i,j) of lbvh_emit_hierarchy_mesh.comp:85-103 for leaves inside [b0-1, b1+1] (up to a monotone map: true clz)
-    auto delta = [&](int i, int j) -> int {
-        const uint32_t x = S.codes[i + 1 - b0] ^ S.codes[j + 1 - b0];
-        return x ? __clz(x) : 32 + __clz((uint32_t)(i ^ j));
+    auto delta_adj = [&](int a) -> int { return (int)S.delta[a + 1 - b0]; };   // a in [b0-1, b1]
+    auto set_parent = [&](uint32_t node, uint32_t parent) {
+        if (node >= (uint32_t)leaf0) reinterpret_cast<uint32_t*>(&S.lq[2][(int)node - leaf0 - b0])[3] = parent;
+        else reinterpret_cast<uint32_t*>(&S.iq[2][(int)node - b0])[3] = parent;
     };
 
-    // ---- T: range and split of internal node i = b0 + tid (FindSpan / FindSplit, :105-168) --------------------------
-    const int i = b0 + tid;
-    bool      local = false, node_is_left = false;
-    int       far_end = i;
-    uint32_t  c0 = kInvalid, c1 = kInvalid;
-    if (valid && i < n - 1)
+    // ---- climb inside the window -----------------------------------------------------------------------------------
+    if (valid)
     {
-        const int d_next = delta(i, i + 1);
-        const int d_prev = i > 0 ? delta(i, i - 1) : -1;
-        const int d      = d_next > d_prev ? 1 : -1;
-        const int dmin   = d > 0 ? d_prev : d_next;
-        // furthest leaf this node may reach: the window's guard leaf (b0-1 or b1+1) if it exists, else the array end
-        const int reach = d > 0 ? min(b1 + 1, n - 1) - i : i - max(b0 - 1, 0);
-        int l = 0;
-#pragma unroll
-        for (int t = kEmitLeaves; t >= 1; t >>= 1)
-            if (l + t <= reach && delta(i, i + (l + t) * d) > dmin) l += t;
-        const int j = i + l * d;
-        local       = j >= b0 && j <= b1;
-        if (local)
+        int      l = j, r = j;
+        uint32_t me = (uint32_t)(leaf0 + j);
+        bool     is_left = (l == 0) || (r != n - 1 && delta_adj(r) > delta_adj(l - 1));
+        while (!(l == 0 && r == n - 1))
         {
-            const int dnode = delta(i, j);
-            int       sp    = 0;
-#pragma unroll
-            for (int t = kEmitLeaves / 2; t >= 1; t >>= 1)
-                if (sp + t < l && delta(i, i + (sp + t) * d) > dnode) sp += t;
-            const int gamma = i + sp * d + min(d, 0);
-            const int lo_end = min(i, j), hi_end = max(i, j);
-            c0 = lo_end == gamma ? (uint32_t)(leaf0 + gamma) : (uint32_t)gamma;
-            c1 = hi_end == gamma + 1 ? (uint32_t)(leaf0 + gamma + 1) : (uint32_t)(gamma + 1);
-            S.ic0[tid]  = c0;
-            S.ic1[tid]  = c1;
-            S.ifar[tid] = (uint32_t)j;
-            far_end      = j;
-            node_is_left = j < i;  // i is the right end of its range
-            if (c0 >= (uint32_t)leaf0) S.leaf_parent[c0 - leaf0 - b0] = (uint32_t)i; else S.iparent[c0 - b0] = (uint32_t)i;
-            if (c1 >= (uint32_t)leaf0) S.leaf_parent[c1 - leaf0 - b0] = (uint32_t)i; else S.iparent[c1 - b0] = (uint32_t)i;
+            const int split = is_left ? r : l - 1;
+            const int slot  = (!is_left && l == b0) ? kEmitLeaves : (is_left && r == b1) ? kEmitLeaves + 1 : split - b0;
+            __threadfence_block();  // my node's image before my arrival
+            const uint32_t other = atomicExch(&S.flag[slot], (uint32_t)(is_left ? l : r));
+            if (slot >= kEmitLeaves || other == kInvalid) break;  // window edge, or first to arrive
+            __threadfence_block();
+            S.flag[slot] = kDone;
+            int      L, R;
+            uint32_t sib;
+            if (is_left) { L = l; R = (int)other; sib = (split + 1 == R) ? (uint32_t)(leaf0 + split + 1) : (uint32_t)(split + 1); }
+            else { L = (int)other; R = r; sib = (L == split) ? (uint32_t)(leaf0 + split) : (uint32_t)split; }
+            float3 slo, shi;
+            image_box<kScene>(S, sib, leaf0, b0, slo, shi);
+            const bool is_root        = (L == 0 && R == n - 1);
+            const bool parent_is_left = !is_root && ((L == 0) || (R != n - 1 && delta_adj(R) > delta_adj(L - 1)));
+            const uint32_t parent = is_root ? 0u : (uint32_t)(parent_is_left ? R : L);
+            const int      pi     = (int)parent - b0;
+            if (is_left)
+            {
+                S.iq[0][pi] = pack(lo, me); S.iq[1][pi] = pack(hi, sib); S.iq[2][pi] = pack(slo, kInvalid); S.iq[3][pi] = pack(shi, 0u);
+            }
+            else
+            {
+                S.iq[0][pi] = pack(slo, sib); S.iq[1][pi] = pack(shi, me); S.iq[2][pi] = pack(lo, kInvalid); S.iq[3][pi] = pack(hi, 0u);
+            }
+            set_parent(me, parent);
+            set_parent(sib, parent);
+            lo = min3(lo, slo);
+            hi = max3(hi, shi);
+            l = L; r = R; me = parent; is_left = parent_is_left;
         }
     }
     __syncthreads();
+    RR_EMIT_STAMP(3);
 
-    // ---- B: fit the local nodes bottom-up in rounds ---------------------------------------------------------------
+    // ---- flush the images, four coalesced 16-byte quads per node -------------------------------------------------------
     {
-        const int  k0 = c0 >= (uint32_t)leaf0 ? kEmitLeaves + (int)(c0 - leaf0) - b0 : (int)c0 - b0;
-        const int  k1 = c1 >= (uint32_t)leaf0 ? kEmitLeaves + (int)(c1 - leaf0) - b0 : (int)c1 - b0;
-        const bool leaf_c0 = c0 >= (uint32_t)leaf0, leaf_c1 = c1 >= (uint32_t)leaf0;
-        bool todo = local;
-        while (true)
+        float4* out_l = reinterpret_cast<float4*>(p.nodes + leaf0 + b0);
+        float4* out_i = reinterpret_cast<float4*>(p.nodes + b0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
         {
-            bool fire = false;
-            if (todo) fire = (leaf_c0 || S.ready[k0]) && (leaf_c1 || S.ready[k1]);
-            if (fire)
-            {
-                const float4 alo = S.box[k0][0], ahi = S.box[k0][1], blo = S.box[k1][0], bhi = S.box[k1][1];
-                S.box[tid][0] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
-                S.box[tid][1] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
-            }
-            // the barrier separates this round's reads of ready[] from the writes below
-            if (__syncthreads_count(fire) == 0) break;
-            if (fire) { S.ready[tid] = 1; todo = false; }
-            __syncthreads();
+            const int q = tid + k * kEmitLeaves;
+            if (q < 4 * cnt) out_l[q] = S.lq[q & 3][q >> 2];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const int q = tid + k * kEmitLeaves;
+            if (q < 4 * cnt && wbits(S.iq[0][q >> 2]) != kInvalid) out_i[q] = S.iq[q & 3][q >> 2];
         }
     }
-
-    // ---- F: flush, four coalesced 16-byte quads per node -------------------------------------------------------------
-    for (int q = tid; q < 4 * cnt; q += kEmitLeaves)
-    {
-        const int i2 = q >> 2, part = q & 3;
-        float4    out;
-        if (kScene)
-        {
-            const float4 b = S.box[kEmitLeaves + i2][part & 1];
-            out = make_float4(b.x, b.y, b.z, __uint_as_float(part == 0 ? kInvalid : part == 1 ? S.leaf_ref[i2] : part == 2 ? S.leaf_parent[i2] : 0u));
-        }
-        else if (part == 3) out = make_float4(0.f, 0.f, 0.f, 0.f);
-        else
-        {
-            const float* b = S.leaf[i2] + 3 * part;
-            out = make_float4(b[0], b[1], b[2], __uint_as_float(part == 0 ? kInvalid : part == 1 ? S.leaf_ref[i2] : S.leaf_parent[i2]));
-        }
-        reinterpret_cast<float4*>(p.nodes + leaf0 + b0)[q] = out;
-    }
-    for (int q = tid; q < 4 * cnt; q += kEmitLeaves)
-    {
-        const int      i2 = q >> 2, part = q & 3;
-        const uint32_t a0 = S.ic0[i2];
-        if (a0 == kInvalid) continue;  // not formed inside this window
-        const uint32_t a1 = S.ic1[i2];
-        const uint32_t c  = part < 2 ? a0 : a1;
-        const int      k  = c >= (uint32_t)leaf0 ? kEmitLeaves + (int)(c - leaf0) - b0 : (int)c - b0;
-        const float4   b  = S.box[k][part & 1];
-        const uint32_t w  = part == 0 ? a0 : part == 1 ? a1 : part == 2 ? S.iparent[i2] : 0u;
-        reinterpret_cast<float4*>(p.nodes + b0)[q] = make_float4(b.x, b.y, b.z, __uint_as_float(w));
-    }
+    RR_EMIT_STAMP(4);
     if (n <= kEmitLeaves) return;  // the whole tree was local
 
-    // ---- H: hand the local roots (parent not in this window) to k_emit_global ----------------------------------------
-    // internal node i covering [far_end, i] (left child) or [i, far_end] (right child); leaf j covering [j, j]
-    const bool has_a = local && S.iparent[tid] == kInvalid;
-    const bool has_b = valid && S.leaf_parent[tid] == kInvalid;
-    uint2      ent_a = make_uint2(0, 0), ent_b = make_uint2(0, 0);
-    if (has_a) ent_a = node_is_left ? make_uint2((uint32_t)i, (uint32_t)far_end) : make_uint2((uint32_t)(i - 1), (uint32_t)far_end);
-    if (has_b)
-    {
-        const bool left = (i == 0) || (i != n - 1 && delta(i, i + 1) > delta(i, i - 1));
-        ent_b = make_uint2((uint32_t)(left ? i : i - 1), (uint32_t)i);
-    }
+    // ---- hand the climbers that are still waiting for a sibling to k_emit_global ---------------------------------------
+    // thread t looks after rendezvous slot t, threads 0 and 1 also after the two window-edge slots
+    const uint32_t far_a = S.flag[tid], far_b = tid < 2 ? S.flag[kEmitLeaves + tid] : kInvalid;
+    const bool     has_a = far_a != kInvalid && far_a != kDone, has_b = far_b != kInvalid && far_b != kDone;
     const uint32_t idx_a = has_a ? atomicAdd(&s_pending_n, 1u) : 0u;
     const uint32_t idx_b = has_b ? atomicAdd(&s_pending_n, 1u) : 0u;
     __syncthreads();
@@ -505,6 +506,8 @@ __global__ void __launch_bounds__(kEmitLeaves, 3) k_emit_fit(EmitParams p)
         __threadfence();
         __syncthreads();
     }
+    const uint2 ent_a = make_uint2((uint32_t)(b0 + tid), far_a);
+    const uint2 ent_b = make_uint2((uint32_t)(tid == 0 ? b0 - 1 : b1), far_b);
     if (has_a)
     {
         if (fits) p.pending[s_pending_base + idx_a] = ent_a;
@@ -515,6 +518,7 @@ __global__ void __launch_bounds__(kEmitLeaves, 3) k_emit_fit(EmitParams p)
         if (fits) p.pending[s_pending_base + idx_b] = ent_b;
         else global_climb<kScene>(p, ent_b.x, ent_b.y);
     }
+    RR_EMIT_STAMP(5);
 }
 
 // Climbers whose sibling lies outside their window: (split, far bound) identifies the node and its range.
@@ -780,6 +784,9 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
     p.codes = sorted_codes; p.refs = sorted_refs; p.n = n; p.flags = flags; p.nodes = nodes; p.mesh = mesh;
     p.pending_count = g_aabb + 7;  // spare word of the scene-AABB block, zeroed with the max half
     p.pending = reinterpret_cast<uint2*>(sc + L.pending_off); p.pending_capacity = L.pending_capacity;
+#ifdef RR_EMIT_TIMELINE
+    p.timeline = reinterpret_cast<unsigned long long*>(sc + L.sort_off + L.sort.tmp_vals_off);  // dead after the sort
+#endif
     launch_emit_fit<false>(s, p);
     *dev.launches += n > (uint32_t)kEmitLeaves ? 2 : 1;
     RR_CUDA_CHECK(cudaGetLastError());
