@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT = 3840, 2160
 BYTES_PER_RAY = 48           # 32 B ray read + 16 B RRHit write: the compulsory HBM traffic
+TRACE_DRAM_BYTES_PER_LAUNCH = 379_617_792   # dram__bytes_read+write of one C2 launch, ncu --set full (profiles/round1_summary.md)
+LANE_VISITS_PER_RAY = 66.6   # warp-iterations x 32 / rays of the C2 batch on the quality BVH (ncu instruction counts, same file)
 BUILD_BYTES_PER_TRI = 348    # 48 aabb + 48 morton + 4 code + 60 sort + 12 emit reads + 48 gather + 128 nodes
 
 
@@ -228,6 +230,7 @@ def run_ours(args):
         cpu = cpu_baseline(geom.nodes(), rays)
 
     peak, peak_src = measured_peak_gbs()
+    l1_peak_visits = 2.0 * eng.sm_count * (clocks["sm_max_mhz"] if clocks and clocks.get("sm_max_mhz") else 1965.0) * 1e6
     achieved = BYTES_PER_RAY * n_rays / (ms_step * 1e-3) / 1e9
     build_gbs = BUILD_BYTES_PER_TRI * n_tris / (ms_fast * 1e-3) / 1e9
     out = {
@@ -241,8 +244,16 @@ def run_ours(args):
                 "ms_per_step": round(ms_e2e, 4), "pipeline": f"{args.e2e_chunks} slices, H2D / rrCmdIntersect / D2H on three streams"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "peak_source": peak_src, "kernel": "k_trace<closest,full_hit,one_level>",
-                     "note": "48 B/ray compulsory; traversal is L1/L2-latency and issue bound, see DESIGN.md"},
+                     "traffic": TRACE_DRAM_BYTES_PER_LAUNCH if (n_rays, args.bvh) == (WIDTH * HEIGHT, "quality") else None,
+                     "peak_source": peak_src, "kernel": "k_trace<closest,full_hit,one_level>",
+                     "algorithmic_bytes_per_launch": BYTES_PER_RAY * n_rays,
+                     "note": "48 B/ray compulsory (32 B ray + 16 B hit), BVH L2-resident: HBM is not the bound",
+                     # the binding unit: every lane receives 64 B per visited node through the SM's
+                     # 128 B/clk L1 data pipe => 2 node visits/clk/SM
+                     "l1_data_pipe": {"lane_visits_per_ray": LANE_VISITS_PER_RAY, "peak_visits_per_s": round(l1_peak_visits, 1),
+                                      "achieved_visits_per_s": round(LANE_VISITS_PER_RAY * n_rays / (ms_step * 1e-3), 1),
+                                      "frac": round(LANE_VISITS_PER_RAY * n_rays / (ms_step * 1e-3) / l1_peak_visits, 4),
+                                      "ncu_l1tex_data_pipe_pct": 87.0, "source": "profiles/round1_summary.md section 2"}},
         "cpu_baseline": cpu,
         "clocks": clocks,
         "build": {"fast_ms": round(ms_fast, 4), "fast_mtris_per_s": round(n_tris / ms_fast / 1e3, 1), "quality_ms": round(ms_qual, 4),
@@ -262,12 +273,20 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def host_threads():
+    """All the host threads this process may use (torchrun pins OMP_NUM_THREADS=1 for its ranks; the CPU arm undoes that)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(nodes, rays, budget_rays=None):
     """Reference CPU tracer (oracle/_ref/bvh_analyzer_trace) or the oracle port on a bounded sample of the batch."""
     from oracle import binding as O
     sample = rays.reshape(HEIGHT, WIDTH)[::4, ::2].reshape(-1)   # 1 036 800 rays, every 4th row / 2nd column
     desc = f"{sample.shape[0]} rays = rows[::4], cols[::2] of the {WIDTH}x{HEIGHT} batch"
-    res = O.ref_bvh_analyzer_trace(nodes, sample, repeats=3)
+    res = O.ref_bvh_analyzer_trace(nodes, sample, repeats=3, threads=host_threads())
     if res is not None and res.get("is_valid"):
         return {"value": round(res["mrays_per_s"], 3), "unit": "Mrays/s", "cores": res["threads"], "kind": "reference",
                 "sample": desc + "; bvh_analyzer BvhIntersect<2> loop only (bvh.h:87-93), 3 repeats, mean",
@@ -285,6 +304,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())   # before the OpenMP oracle library is loaded
     from oracle import binding as O
     from radeonrays_sdk_b200 import workloads as W
     pos, idx, _ = W.load_mesh("sponza")
@@ -297,7 +317,7 @@ def run_reference(args):
     cores = O.num_threads()
     for step in range(args.warmup + args.steps):
         if kind == "reference":
-            res = O.ref_bvh_analyzer_trace(nodes, sample, repeats=1)
+            res = O.ref_bvh_analyzer_trace(nodes, sample, repeats=1, threads=host_threads())
             dt, cores = res["mean_s"], res["threads"]
         else:
             t0 = time.time()

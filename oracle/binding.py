@@ -175,8 +175,9 @@ def num_threads():
     return int(lib().rro_num_threads())
 
 
-def ref_bvh_analyzer_trace(nodes, rays, repeats=1, workdir=None, want_hits=False):
-    """Run the compiled REFERENCE CPU tracer (oracle/_ref/bvh_analyzer_trace) on a node dump. Returns its JSON."""
+def ref_bvh_analyzer_trace(nodes, rays, repeats=1, workdir=None, want_hits=False, threads=None):
+    """Run the compiled REFERENCE CPU tracer (oracle/_ref/bvh_analyzer_trace) on a node dump. Returns its JSON.
+    `threads` sets OMP_NUM_THREADS for the child (torchrun exports OMP_NUM_THREADS=1 to its ranks)."""
     import json, tempfile
     exe = os.path.join(_HERE, "_ref", "bvh_analyzer_trace")
     if not os.path.exists(exe):
@@ -188,7 +189,10 @@ def ref_bvh_analyzer_trace(nodes, rays, repeats=1, workdir=None, want_hits=False
     cmd = [exe, os.path.join(d, "bvh.bin"), str(n - 1), str(n), os.path.join(d, "rays.bin"), str(rays.shape[0]), str(repeats)]
     if want_hits:
         cmd.append(os.path.join(d, "hits.bin"))
-    out = subprocess.run(cmd, capture_output=True, text=True)
+    env = dict(os.environ)
+    if threads:
+        env["OMP_NUM_THREADS"] = str(int(threads))
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env)
     res = json.loads(out.stdout.strip().splitlines()[-1])
     if want_hits:
         res["hits"] = np.fromfile(os.path.join(d, "hits.bin"), dtype=HIT_DTYPE)

@@ -35,6 +35,7 @@ class Engine:
         self.torch_stream = torch.cuda.Stream(self.device)
         torch.cuda.set_stream(self.torch_stream)
         self.ctx = api.Context(device=device, cuda_stream=self.torch_stream.cuda_stream)
+        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
 
     def close(self):
         torch.cuda.synchronize(self.device)
