@@ -12,6 +12,7 @@
 // Algorithmic HBM bytes per triangle (u32 indices, 12-B vertices): aabb 48 + morton 48 + code write 4 +
 // sort 60 (identity values: no ref write/read in pass 0) + emit/fit: codes 8, refs 4, gather 48, nodes 128.
 #include <algorithm>
+#include <cstdlib>
 
 #include "rr_internal.h"
 
@@ -189,7 +190,7 @@ struct EmitParams
     uint32_t*       pending_count;     // preset to 0: climbers handed from the local to the global kernel
     uint2*          pending;           // [pending_capacity] (split position, far bound) of each
     uint32_t        pending_capacity;
-    unsigned long long* timeline;      // debug (RR_EMIT_TIMELINE builds): 8 timestamps per sampled CTA
+    uint32_t*       masks;             // [ceil(n/32)] per 32 leaves: left ends of the subtrees k_emit_leaves left over
     // mesh leaves
     MeshDesc mesh;
     // scene leaves
@@ -234,38 +235,33 @@ __device__ __forceinline__ void affine_inverse(const float* m, float4& r0, float
     r2 = make_float4(r20, r21, r22, -((r20 * tx + r21 * ty) + r22 * tz));
 }
 
-// Hierarchy emission + box fitting in one pass; every node's 64 bytes are written once.
+// Hierarchy emission + box fitting fused; every node's 64 bytes are written once (plus its parent word when the parent
+// is formed by a later step).
 //
 // Node numbering (Karras 2012, lbvh_emit_hierarchy_mesh.comp:105-217): internal node i covers a range of sorted leaves
 // that has i at one end; a non-root internal node sits at the RIGHT end of its range if it is a left child (it is its
 // parent's split position) and at the LEFT end if it is a right child (split+1); the root is 0; leaf j is node N-1+j.
+// The hierarchy over any run of consecutive, already finished subtrees ("elements") is the Cartesian tree of the deltas
+// between neighbours: the node split right of element s spans the elements between the nearest smaller delta on either
+// side -- the range FindSpan/FindSplit find by binary search from the node's own index.  Every subtree that lies inside
+// a run of leaves also has its internal node indices inside that run.
 //
-// B200 mapping (two kernels):
-//   k_emit_fit   -- a CTA owns a window of kEmitLeaves consecutive sorted leaves.  Every subtree that lies inside the
-//     window also has its internal node indices inside the window, so the classic bottom-up construction runs entirely
-//     on shared memory: one climber per leaf owns a range [l,r] and the node covering it; the range is a left child iff
-//     delta(r,r+1) > delta(l-1,l); both children meet at the rendezvous word of their split position -- the first to
-//     arrive leaves its far bound and retires, the second learns the sibling's bound, hence the parent's range and its
-//     Karras index, writes the parent's finished 64-byte image into shared memory and climbs on.  The images leave as
-//     fully coalesced 16-byte quads (each node byte is written to HBM exactly once); climbers whose sibling lies outside
-//     the window (~2 log2(window) per CTA) are handed to k_emit_global as (split position, far bound) pairs.
-//   k_emit_global -- one thread per handed-over climber continues the same protocol on global rendezvous words,
-//     reading sibling boxes back with ld.cg.
-// Keeping the long climbs out of k_emit_fit matters: a CTA that waited for its one climber to reach the root held its
-// thread slots for ~50 us and the single-kernel version ran 7 ms for 50 M triangles (profiles/round1_summary.md lists
-// the variants that were measured: barrier-paced rounds, flag polling, a one-warp tail, 256-leaf windows).
-constexpr int      kEmitLeaves = 512;  // leaves (= threads) per CTA
-constexpr uint32_t kDone       = 0xFFFFFFFEu;
-
-struct EmitSmem
-{
-    // node images, quad-major (quad k of node i at [k][i], one pad entry per row): a thread touching "its" node is
-    // bank-conflict free and the flush is a plain copy
-    float4   iq[4][kEmitLeaves + 1];   // internal nodes b0 .. b0+511; [0][i].w == INVALID: not formed in this window
-    float4   lq[4][kEmitLeaves + 1];   // leaves b0 .. b0+511
-    uint32_t flag[kEmitLeaves + 2];    // rendezvous per local split; [kEmitLeaves] / [+1]: climber stopped at the left / right window edge
-    uint8_t  delta[kEmitLeaves + 2];   // delta(a, a+1) for a = b0-1 .. b1
-};
+// B200 mapping (three kernels, no barriers, no shared-memory images):
+//   k_emit_leaves -- one warp per 32 consecutive sorted leaves.  group_merge() forms, in closed form and with ballots and
+//     shuffles only, EVERY node whose range lies inside the 32 leaves (~85 % of all internal nodes): range, Karras index,
+//     child ids, parent index, and both child boxes as range min/max over the lanes.  Leaves and nodes go straight to HBM
+//     (64 B per lane, full sectors); what cannot be decided inside the group -- its maximal subtrees -- is recorded as one
+//     32-bit mask of left ends.  Warps are independent, so memory latency of the gather (ref -> indices -> vertices) is
+//     hidden by the other warps of the SM like in any streaming kernel.
+//   k_emit_window -- one warp per 512-leaf window repeats group_merge() over the left-over subtrees of its 16 groups
+//     (boxes read back from the node images, L2), 32 at a time, until one group holds them all (2-3 passes).
+//   k_emit_global -- the ~2 % of subtrees whose sibling lies outside their window finish with the classic atomic
+//     rendezvous protocol on global words, one thread per subtree.
+// profiles/round1_summary.md lists the variants measured before this one (single kernel with global atomics; 512-leaf
+// CTA windows with shared-memory images and an atomic climb; barrier-paced rounds; ...): all were bound by the serial
+// gather -> climb -> flush chain of a CTA at 1 536 resident threads per SM.
+constexpr int      kEmitWindow    = 512;  // leaves per k_emit_window warp
+constexpr int      kEmitMaxPasses = 64;
 
 // The rendezvous protocol on the global words, for a node that is already in memory.  (split, far) identify it: the
 // climber covers [far, split] if it is a left child (far <= split), else [split+1, far].
@@ -318,207 +314,316 @@ __device__ void global_climb(const EmitParams& p, uint32_t split, uint32_t far)
     }
 }
 
-// Box of a node from its shared-memory image.
-template <bool kScene>
-__device__ __forceinline__ void image_box(const EmitSmem& S, uint32_t node, int leaf0, int b0, float3& lo, float3& hi)
+
+// A whole 64-byte node as two 32-byte stores (STG.E.256): every lane writes full sectors.
+__device__ __forceinline__ void st_node(Node* dst, float4 q0, float4 q1, float4 q2, float4 q3)
 {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(q0.x), "f"(q0.y), "f"(q0.z), "f"(q0.w), "f"(q1.x),
+                 "f"(q1.y), "f"(q1.z), "f"(q1.w)
+                 : "memory");
+    asm volatile("st.global.v8.f32 [%0+32], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(q2.x), "f"(q2.y), "f"(q2.z), "f"(q2.w),
+                 "f"(q3.x), "f"(q3.y), "f"(q3.z), "f"(q3.w)
+                 : "memory");
+}
+
+// Range min (kMin) / max over lanes [Ll, lane] -> outL and [lane+1, pr] -> outR of a per-lane value: four doubling
+// steps build the windows "2^k lanes ending here", the two ranges are then covered by the binary digits of their lengths.
+template <bool kMin>
+__device__ __forceinline__ void lane_range_reduce(float x, int lane, int lenL, int pr, int lenR, float& outL, float& outR)
+{
+    const uint32_t full = 0xffffffffu;
+    auto op = [](float p, float q) { return kMin ? fminf(p, q) : fmaxf(p, q); };
+    float t[5];
+    t[0] = x;
+#pragma unroll
+    for (int k = 1; k < 5; ++k) t[k] = op(t[k - 1], __shfl_up_sync(full, t[k - 1], 1 << (k - 1)));
+    float accL = kMin ? __int_as_float(0x7f800000) : __int_as_float(0xff800000), accR = accL;
+    int   pL = lane, pR = pr;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+    {
+        const float u = __shfl_sync(full, t[k], pL & 31);
+        const float v = __shfl_sync(full, t[k], pR & 31);
+        if (lenL & (1 << k)) { accL = op(accL, u); pL -= 1 << k; }
+        if (lenR & (1 << k)) { accR = op(accR, v); pR -= 1 << k; }
+    }
+    outL = accL;
+    outR = accR;
+}
+
+struct MergeOut
+{
+    bool     e_over;      // this lane's element is still a top-level subtree (its parent is not formed here, it is not the root)
+    uint32_t e_parent;    // its parent's index when that was formed here, else INVALID
+    bool     n_over;      // the node this lane formed is a top-level subtree ...
+    int      n_a;         // ... starting at this sorted leaf
+    bool     any_formed;  // warp-uniform
+};
+
+// One group of up to 32 consecutive top-level subtrees ("elements": sorted leaves [a,b], node id, box), one per lane;
+// D = delta(b, b+1), DL0 = delta left of the first element.  Forms every node whose range lies inside the group and
+// writes its 64 bytes (parent word included when the parent is formed here as well, else INVALID).
+__device__ __forceinline__ MergeOut group_merge(Node* __restrict__ nodes, int n, int cnt, bool valid, int a, int b, uint32_t id, float3 lo,
+                                                float3 hi, int D, int DL0)
+{
+    const uint32_t full  = 0xffffffffu;
+    const int      lane  = threadIdx.x & 31;
+    const uint32_t vmask = cnt >= 32 ? full : ((1u << cnt) - 1u);
+    const uint32_t below = (1u << lane) - 1u, above = ~((2u << lane) - 1u);
+    if (!valid) D = 0;
+    // lanes whose delta is smaller than mine (deltas fit 6 bits: radix compare over bit planes)
+    uint32_t lt = 0, eq = full;
+#pragma unroll
+    for (int bit = 5; bit >= 0; --bit)
+    {
+        const bool     mine = (D >> bit) & 1;
+        const uint32_t B    = __ballot_sync(full, mine);
+        if (mine) { lt |= eq & ~B; eq &= B; }
+        else eq &= ~B;
+    }
+    lt &= vmask;
+    const uint32_t lmask = lt & below, rmask = lt & above;
+    const int      pl = lmask ? 31 - __clz(lmask) : -1;          // nearest smaller delta to the left (-1: the group's left border)
+    const int      pr = rmask ? __ffs(rmask) - 1 : lane;         // ... to the right
+    const bool     formed = lane + 1 < cnt && (lmask != 0 || DL0 < D) && rmask != 0;
+    const uint32_t IG = __ballot_sync(full, formed);
+    const int      Ll = pl + 1;
+    const int      aL = __shfl_sync(full, a, Ll & 31);
+    const int      bR = __shfl_sync(full, b, pr);
+    int            Dpl = __shfl_sync(full, D, pl < 0 ? 0 : pl);
+    if (pl < 0) Dpl = DL0;
+    const int      Dpr = __shfl_sync(full, D, pr);
+    const bool     is_root = aL == 0 && bR == n - 1;
+    const bool     nleft   = Dpr > Dpl;                           // left child iff delta(R,R+1) > delta(L-1,L)
+    const uint32_t idx = is_root ? 0u : (uint32_t)(nleft ? bR : aL);
+    const int      q   = nleft ? pr : pl;                         // split lane of the parent
+    const bool     parent_in = formed && !is_root && q >= 0 && ((IG >> (q & 31)) & 1u);
+    const uint32_t pidx = __shfl_sync(full, idx, parent_in ? q : lane);
+    const uint32_t nid  = __shfl_down_sync(full, id, 1);
+    const uint32_t c0 = (Ll == lane) ? id : (uint32_t)b;          // Karras: left child = split, right child = split + 1
+    const uint32_t c1 = (pr == lane + 1) ? nid : (uint32_t)(b + 1);
+    float3 loL, hiL, loR, hiR;
+    {
+        const int lenL = lane - Ll + 1, lenR = pr - lane;
+        lane_range_reduce<true>(lo.x, lane, lenL, pr, lenR, loL.x, loR.x);
+        lane_range_reduce<true>(lo.y, lane, lenL, pr, lenR, loL.y, loR.y);
+        lane_range_reduce<true>(lo.z, lane, lenL, pr, lenR, loL.z, loR.z);
+        lane_range_reduce<false>(hi.x, lane, lenL, pr, lenR, hiL.x, hiR.x);
+        lane_range_reduce<false>(hi.y, lane, lenL, pr, lenR, hiL.y, hiR.y);
+        lane_range_reduce<false>(hi.z, lane, lenL, pr, lenR, hiL.z, hiR.z);
+    }
+    if (formed)
+        st_node(nodes + idx, pack(loL, c0), pack(hiL, c1), pack(loR, parent_in ? pidx : kInvalid), pack(hiR, 0u));
+
+    // the elements themselves: parent = the node split at the larger of the two neighbouring deltas
+    int Dprev = __shfl_up_sync(full, D, 1);
+    if (lane == 0) Dprev = DL0;
+    const int      qe = D > Dprev ? lane : lane - 1;
+    const bool     e_parent_in = valid && qe >= 0 && ((IG >> (qe & 31)) & 1u);
+    const uint32_t pidx_e = __shfl_sync(full, idx, e_parent_in ? qe : lane);
+    MergeOut o;
+    o.e_parent   = e_parent_in ? pidx_e : kInvalid;
+    o.e_over     = valid && !e_parent_in && !(a == 0 && b == n - 1);
+    o.n_over     = formed && !parent_in && !is_root;
+    o.n_a        = aL;
+    o.any_formed = IG != 0;
+    return o;
+}
+
+__device__ __forceinline__ int delta_of(uint32_t ca, uint32_t cb, int a)  // delta(a, a+1) from the two codes
+{
+    const uint32_t x = ca ^ cb;
+    return x ? __clz(x) : 32 + __clz((uint32_t)(a ^ (a + 1)));
+}
+
+// ---- level 1: one warp per 32 sorted leaves ---------------------------------------------------------------------------
+template <bool kScene, int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas) k_emit_leaves(EmitParams p)
+{
+    const uint32_t full = 0xffffffffu;
+    const int n = (int)p.n, leaf0 = n - 1, lane = threadIdx.x & 31;
+    const int ngroups = (n + 31) >> 5, nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroups; g += nwarps)
+    {
+        const int  wb = g << 5, j = wb + lane, cnt = min(32, n - wb);
+        const bool valid = j < n;
+        // deltas (0 outside the array: smaller than every real delta, 30-bit codes have clz >= 2)
+        const uint32_t c  = valid ? p.codes[j] : 0u;
+        uint32_t       cn = __shfl_down_sync(full, c, 1);
+        if (lane == 31 && j + 1 < n) cn = p.codes[j + 1];
+        const int D = (valid && j + 1 < n) ? delta_of(c, cn, j) : 0;
+        int       DL0 = (lane == 0 && wb > 0) ? delta_of(p.codes[wb - 1], c, wb - 1) : 0;
+        DL0 = __shfl_sync(full, DL0, 0);
+        // gather the leaf
+        float3   lo = make_float3(0.f, 0.f, 0.f), hi = lo;
+        float4   q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
+        if (valid)
+        {
+            const uint32_t ref = p.refs[j];
+            if (kScene)
+            {   // lbvh_fit_aabb_scene.comp:113-130
+                const float4 bmin = p.boxes[2 * (size_t)ref], bmax = p.boxes[2 * (size_t)ref + 1];
+                lo = xyz(bmin);
+                hi = xyz(bmax);
+                const InstanceDesc d = p.descs[ref];
+                InstanceRecord rec;
+                affine_inverse(d.m, rec.inv0, rec.inv1, rec.inv2);
+                rec.blas = d.blas;
+                rec.pad  = 0;
+                p.records[ref]             = rec;
+                p.fwd[3 * (size_t)ref + 0] = make_float4(d.m[0], d.m[1], d.m[2], d.m[3]);
+                p.fwd[3 * (size_t)ref + 1] = make_float4(d.m[4], d.m[5], d.m[6], d.m[7]);
+                p.fwd[3 * (size_t)ref + 2] = make_float4(d.m[8], d.m[9], d.m[10], d.m[11]);
+                q0 = pack(lo, kInvalid); q1 = pack(hi, ref); q2 = pack(lo, kInvalid); q3 = pack(hi, 0u);
+            }
+            else
+            {   // lbvh_fit_aabb_mesh.comp:139-163
+                const uint32_t i0 = p.mesh.indices[3 * (size_t)ref + 0], i1 = p.mesh.indices[3 * (size_t)ref + 1],
+                               i2 = p.mesh.indices[3 * (size_t)ref + 2];
+                const float3 v0 = ld3(p.mesh.vertices + (size_t)i0 * p.mesh.stride_floats);
+                const float3 v1 = ld3(p.mesh.vertices + (size_t)i1 * p.mesh.stride_floats);
+                const float3 v2 = ld3(p.mesh.vertices + (size_t)i2 * p.mesh.stride_floats);
+                lo = min3(min3(v0, v1), v2);
+                hi = max3(max3(v0, v1), v2);
+                q0 = pack(v0, kInvalid); q1 = pack(v1, ref); q2 = pack(v2, kInvalid);
+            }
+        }
+        const MergeOut o = group_merge(p.nodes, n, cnt, valid, j, j, (uint32_t)(leaf0 + j), lo, hi, D, DL0);
+        if (valid) st_node(p.nodes + leaf0 + j, q0, q1, make_float4(q2.x, q2.y, q2.z, __uint_as_float(o.e_parent)), q3);
+        const uint32_t mask = __ballot_sync(full, o.e_over) | __reduce_or_sync(full, o.n_over ? 1u << ((o.n_a - wb) & 31) : 0u);
+        if (lane == 0) p.masks[g] = mask;
+    }
+}
+
+// Box of a finished node from its image in memory (L2).
+template <bool kScene>
+__device__ __forceinline__ void node_box_ldcg(const Node* nodes, uint32_t node, int leaf0, float3& lo, float3& hi)
+{
+    const float4* np = reinterpret_cast<const float4*>(nodes + node);
+    const float4  q0 = __ldcg(np), q1 = __ldcg(np + 1), q2 = __ldcg(np + 2);
     if (node >= (uint32_t)leaf0)
     {
-        const int k = (int)node - leaf0 - b0;
-        const float4 q0 = S.lq[0][k], q1 = S.lq[1][k];
         if (kScene) { lo = xyz(q0); hi = xyz(q1); }
         else
         {
-            const float4 q2 = S.lq[2][k];
             lo = min3(min3(xyz(q0), xyz(q1)), xyz(q2));
             hi = max3(max3(xyz(q0), xyz(q1)), xyz(q2));
         }
     }
     else
     {
-        const int k = (int)node - b0;
-        lo = min3(xyz(S.iq[0][k]), xyz(S.iq[2][k]));
-        hi = max3(xyz(S.iq[1][k]), xyz(S.iq[3][k]));
+        const float4 q3 = __ldcg(np + 3);
+        lo = min3(xyz(q0), xyz(q2));
+        hi = max3(xyz(q1), xyz(q3));
     }
 }
 
+// ---- level 2: one warp per 512-leaf window, over what its 16 groups left over --------------------------------------------
+constexpr int kWindowWarps = 8;  // per CTA
 template <bool kScene>
-__global__ void __launch_bounds__(kEmitLeaves, 3) k_emit_fit(EmitParams p)
+__global__ void __launch_bounds__(32 * kWindowWarps) k_emit_window(EmitParams p)
 {
-    extern __shared__ __align__(16) unsigned char emit_smem_raw[];
-    EmitSmem& S = *reinterpret_cast<EmitSmem*>(emit_smem_raw);
-    __shared__ uint32_t s_pending_n, s_pending_base;
-    const int  n = (int)p.n, leaf0 = n - 1;
-    const int  tid = threadIdx.x;
-    const int  b0  = blockIdx.x * kEmitLeaves;
-    const int  cnt = min(kEmitLeaves, n - b0);
-    const int  b1  = b0 + cnt - 1;
-    const bool valid = tid < cnt;
-    const int  j = b0 + tid;  // this thread's leaf
-    // phase timeline of every 64th CTA (tools/emit_timeline.py), compiled in with -DRR_EMIT_TIMELINE
-#ifdef RR_EMIT_TIMELINE
-#define RR_EMIT_STAMP(k) do { if (p.timeline && tid == 0 && (blockIdx.x & 63) == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.timeline[(blockIdx.x >> 6) * 8 + (k)] = t_; } } while (0)
-#else
-#define RR_EMIT_STAMP(k) do { } while (0)
-#endif
-    RR_EMIT_STAMP(0);
-
-    // delta(a, a+1), a = b0-1+k (lbvh_emit_hierarchy_mesh.comp:85-103 up to a monotone map: true clz); fits a byte
-    for (int k = tid; k < cnt + 1; k += kEmitLeaves)
+    __shared__ uint8_t  s_delta[kWindowWarps][kEmitWindow + 8];  // delta(a, a+1) for a = b0-1 .. b1
+    __shared__ uint32_t s_mask[kWindowWarps][2][kEmitWindow / 32];
+    __shared__ uint16_t s_list[kWindowWarps][kEmitWindow + 2];  // left ends (relative to b0) of the current elements, ascending
+    const uint32_t full = 0xffffffffu;
+    const int n = (int)p.n, leaf0 = n - 1, lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int w = blockIdx.x * kWindowWarps + wi;
+    const int b0 = w * kEmitWindow;
+    if (b0 >= n) return;
+    const int cnt = min(kEmitWindow, n - b0), b1 = b0 + cnt - 1;
+    uint8_t*  delta = s_delta[wi];
+    for (int k = lane; k < cnt + 1; k += 32)
     {
         const int a = b0 - 1 + k;
-        uint32_t  d = 0;
-        if (a >= 0 && a + 1 < n)
+        delta[k] = (uint8_t)((a >= 0 && a + 1 < n) ? delta_of(p.codes[a], p.codes[a + 1], a) : 0);
+    }
+    auto delta_adj = [&](int a) -> int { return (int)delta[a + 1 - b0]; };   // a in [b0-1, b1]
+    const int ngrp = (cnt + 31) >> 5;
+    if (lane < kEmitWindow / 32) s_mask[wi][0][lane] = lane < ngrp ? p.masks[(b0 >> 5) + lane] : 0u;
+    __syncwarp();
+
+    int       cur = 0, M = 0;
+    uint16_t* list = s_list[wi];
+    // expands the current mask words into the ordered list of left ends; list[M] = one past the window
+    auto load_masks = [&]() {
+        uint32_t m    = lane < kEmitWindow / 32 ? s_mask[wi][cur][lane] : 0u;
+        uint32_t incl = __popc(m);
+#pragma unroll
+        for (int d = 1; d < kEmitWindow / 32; d <<= 1)
         {
-            const uint32_t x = p.codes[a] ^ p.codes[a + 1];
-            d = x ? __clz(x) : 32 + __clz((uint32_t)(a ^ (a + 1)));
+            const uint32_t t = __shfl_up_sync(full, incl, d);
+            if (lane >= d) incl += t;
         }
-        S.delta[k] = (uint8_t)d;
-    }
-    if (tid == 0) s_pending_n = 0;
-    S.flag[tid] = kInvalid;
-    if (tid < 2) S.flag[kEmitLeaves + tid] = kInvalid;
-    reinterpret_cast<uint32_t*>(&S.iq[0][tid])[3] = kInvalid;  // not formed (yet)
-
-    // ---- leaves: gather, build the leaf image, keep the box in registers ------------------------------------------
-    float3 lo = make_float3(0.f, 0.f, 0.f), hi = lo;
-    if (valid)
-    {
-        const uint32_t ref = p.refs[j];
-        if (kScene)
-        {   // lbvh_fit_aabb_scene.comp:113-130
-            const float4 bmin = p.boxes[2 * (size_t)ref], bmax = p.boxes[2 * (size_t)ref + 1];
-            lo = xyz(bmin);
-            hi = xyz(bmax);
-            const InstanceDesc d = p.descs[ref];
-            InstanceRecord rec;
-            affine_inverse(d.m, rec.inv0, rec.inv1, rec.inv2);
-            rec.blas = d.blas;
-            rec.pad  = 0;
-            p.records[ref]             = rec;
-            p.fwd[3 * (size_t)ref + 0] = make_float4(d.m[0], d.m[1], d.m[2], d.m[3]);
-            p.fwd[3 * (size_t)ref + 1] = make_float4(d.m[4], d.m[5], d.m[6], d.m[7]);
-            p.fwd[3 * (size_t)ref + 2] = make_float4(d.m[8], d.m[9], d.m[10], d.m[11]);
-            S.lq[0][tid] = pack(lo, kInvalid);
-            S.lq[1][tid] = pack(hi, ref);
-            S.lq[2][tid] = pack(lo, kInvalid);
-            S.lq[3][tid] = pack(hi, 0u);
+        int k = (int)(incl - __popc(m));
+        M     = (int)__shfl_sync(full, incl, kEmitWindow / 32 - 1);
+        while (m)
+        {
+            list[k++] = (uint16_t)(32 * lane + __ffs(m) - 1);
+            m &= m - 1;
         }
-        else
-        {   // lbvh_fit_aabb_mesh.comp:139-163
-            const uint32_t i0 = p.mesh.indices[3 * (size_t)ref + 0], i1 = p.mesh.indices[3 * (size_t)ref + 1],
-                           i2 = p.mesh.indices[3 * (size_t)ref + 2];
-            const float3 v0 = ld3(p.mesh.vertices + (size_t)i0 * p.mesh.stride_floats);
-            const float3 v1 = ld3(p.mesh.vertices + (size_t)i1 * p.mesh.stride_floats);
-            const float3 v2 = ld3(p.mesh.vertices + (size_t)i2 * p.mesh.stride_floats);
-            lo = min3(min3(v0, v1), v2);
-            hi = max3(max3(v0, v1), v2);
-            S.lq[0][tid] = pack(v0, kInvalid);
-            S.lq[1][tid] = pack(v1, ref);
-            S.lq[2][tid] = pack(v2, kInvalid);
-            S.lq[3][tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-    __syncthreads();
-    RR_EMIT_STAMP(1);
-
-    auto delta_adj = [&](int a) -> int { return (int)S.delta[a + 1 - b0]; };   // a in [b0-1, b1]
-    auto set_parent = [&](uint32_t node, uint32_t parent) {
-        if (node >= (uint32_t)leaf0) reinterpret_cast<uint32_t*>(&S.lq[2][(int)node - leaf0 - b0])[3] = parent;
-        else reinterpret_cast<uint32_t*>(&S.iq[2][(int)node - b0])[3] = parent;
+        if (lane == 0) list[M] = (uint16_t)cnt;
+        __syncwarp();
     };
-
-    // ---- climb inside the window -----------------------------------------------------------------------------------
-    if (valid)
+    auto left_end = [&](int r) -> int { return b0 + (int)list[min(r, M)]; };
+    load_masks();
+    bool prev_formed = true;
+    for (int pass = 1; M > 1 && pass < kEmitMaxPasses; ++pass)
     {
-        int      l = j, r = j;
-        uint32_t me = (uint32_t)(leaf0 + j);
-        bool     is_left = (l == 0) || (r != n - 1 && delta_adj(r) > delta_adj(l - 1));
-        while (!(l == 0 && r == n - 1))
+        // every other pass shifts the grouping by half a group, so that siblings on either side of a border meet
+        const int off = (M > 32 && (pass & 1)) ? 16 : 0;
+        const int ngroups = off ? 1 + (M - 16 + 31) / 32 : (M + 31) / 32;
+        if (lane < kEmitWindow / 32) s_mask[wi][cur ^ 1][lane] = 0u;
+        __syncwarp();
+        bool any = false;
+        for (int g = 0; g < ngroups; ++g)
         {
-            const int split = is_left ? r : l - 1;
-            const int slot  = (!is_left && l == b0) ? kEmitLeaves : (is_left && r == b1) ? kEmitLeaves + 1 : split - b0;
-            __threadfence_block();  // my node's image before my arrival
-            const uint32_t other = atomicExch(&S.flag[slot], (uint32_t)(is_left ? l : r));
-            if (slot >= kEmitLeaves || other == kInvalid) break;  // window edge, or first to arrive
-            __threadfence_block();
-            S.flag[slot] = kDone;
-            int      L, R;
-            uint32_t sib;
-            if (is_left) { L = l; R = (int)other; sib = (split + 1 == R) ? (uint32_t)(leaf0 + split + 1) : (uint32_t)(split + 1); }
-            else { L = (int)other; R = r; sib = (L == split) ? (uint32_t)(leaf0 + split) : (uint32_t)split; }
-            float3 slo, shi;
-            image_box<kScene>(S, sib, leaf0, b0, slo, shi);
-            const bool is_root        = (L == 0 && R == n - 1);
-            const bool parent_is_left = !is_root && ((L == 0) || (R != n - 1 && delta_adj(R) > delta_adj(L - 1)));
-            const uint32_t parent = is_root ? 0u : (uint32_t)(parent_is_left ? R : L);
-            const int      pi     = (int)parent - b0;
-            if (is_left)
+            const int  e0 = off ? (g == 0 ? 0 : 16 + (g - 1) * 32) : g * 32;
+            const int  e1 = min(M, off && g == 0 ? 16 : e0 + 32);
+            const int  e  = e0 + lane;
+            const bool v  = e < e1;
+            const int  a = left_end(e);                        // (b1 + 1 for lanes past the end)
+            const int  b = v ? left_end(e + 1) - 1 : a;
+            uint32_t   id = 0;
+            float3     elo = make_float3(0.f, 0.f, 0.f), ehi = elo;
+            if (v)
             {
-                S.iq[0][pi] = pack(lo, me); S.iq[1][pi] = pack(hi, sib); S.iq[2][pi] = pack(slo, kInvalid); S.iq[3][pi] = pack(shi, 0u);
+                id = a == b ? (uint32_t)(leaf0 + a) : (uint32_t)(delta_adj(b) > delta_adj(a - 1) ? b : a);
+                node_box_ldcg<kScene>(p.nodes, id, leaf0, elo, ehi);
             }
-            else
-            {
-                S.iq[0][pi] = pack(slo, sib); S.iq[1][pi] = pack(shi, me); S.iq[2][pi] = pack(lo, kInvalid); S.iq[3][pi] = pack(hi, 0u);
-            }
-            set_parent(me, parent);
-            set_parent(sib, parent);
-            lo = min3(lo, slo);
-            hi = max3(hi, shi);
-            l = L; r = R; me = parent; is_left = parent_is_left;
+            const int a_first = __shfl_sync(full, a, 0);
+            const MergeOut o = group_merge(p.nodes, n, e1 - e0, v, a, b, id, elo, ehi, v ? delta_adj(b) : 0, delta_adj(a_first - 1));
+            if (v && o.e_parent != kInvalid) reinterpret_cast<uint32_t*>(p.nodes + id)[11] = o.e_parent;  // q2.w
+            if (o.e_over) atomicOr(&s_mask[wi][cur ^ 1][(a - b0) >> 5], 1u << ((a - b0) & 31));
+            if (o.n_over) atomicOr(&s_mask[wi][cur ^ 1][(o.n_a - b0) >> 5], 1u << ((o.n_a - b0) & 31));
+            any |= o.any_formed;
         }
+        __syncwarp();
+        cur ^= 1;
+        load_masks();
+        if (ngroups == 1 || (!any && !prev_formed)) break;
+        prev_formed = any;
     }
-    __syncthreads();
-    RR_EMIT_STAMP(3);
+    if (n <= kEmitWindow) return;  // the whole tree was local
 
-    // ---- flush the images, four coalesced 16-byte quads per node -------------------------------------------------------
+    // ---- hand the subtrees whose sibling lies outside the window to k_emit_global as (split, far bound) ---------------
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(p.pending_count, (uint32_t)M);
+    base = __shfl_sync(full, base, 0);
+    const bool fits = base + (uint32_t)M <= p.pending_capacity;
+    if (!fits) __threadfence();  // list full (it holds n/4 entries; a window hands over ~2 log2(512)): finish the climbs here
+    for (int e0 = 0; e0 < M; e0 += 32)
     {
-        float4* out_l = reinterpret_cast<float4*>(p.nodes + leaf0 + b0);
-        float4* out_i = reinterpret_cast<float4*>(p.nodes + b0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
+        const int  e = e0 + lane;
+        if (e < M)
         {
-            const int q = tid + k * kEmitLeaves;
-            if (q < 4 * cnt) out_l[q] = S.lq[q & 3][q >> 2];
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-        {
-            const int q = tid + k * kEmitLeaves;
-            if (q < 4 * cnt && wbits(S.iq[0][q >> 2]) != kInvalid) out_i[q] = S.iq[q & 3][q >> 2];
+            const int   a = left_end(e), b = left_end(e + 1) - 1;
+            const bool  is_left = delta_adj(b) > delta_adj(a - 1);
+            const uint2 ent = is_left ? make_uint2((uint32_t)b, (uint32_t)a) : make_uint2((uint32_t)(a - 1), (uint32_t)b);
+            if (fits) p.pending[base + e] = ent;
+            else global_climb<kScene>(p, ent.x, ent.y);
         }
     }
-    RR_EMIT_STAMP(4);
-    if (n <= kEmitLeaves) return;  // the whole tree was local
-
-    // ---- hand the climbers that are still waiting for a sibling to k_emit_global ---------------------------------------
-    // thread t looks after rendezvous slot t, threads 0 and 1 also after the two window-edge slots
-    const uint32_t far_a = S.flag[tid], far_b = tid < 2 ? S.flag[kEmitLeaves + tid] : kInvalid;
-    const bool     has_a = far_a != kInvalid && far_a != kDone, has_b = far_b != kInvalid && far_b != kDone;
-    const uint32_t idx_a = has_a ? atomicAdd(&s_pending_n, 1u) : 0u;
-    const uint32_t idx_b = has_b ? atomicAdd(&s_pending_n, 1u) : 0u;
-    __syncthreads();
-    if (tid == 0) s_pending_base = s_pending_n ? atomicAdd(p.pending_count, s_pending_n) : 0u;
-    __syncthreads();
-    const bool fits = s_pending_base + s_pending_n <= p.pending_capacity;
-    if (!fits)
-    {   // list full (never seen: it holds n/4 entries and a window hands over ~2 log2(512)): finish the climbs here
-        __threadfence();
-        __syncthreads();
-    }
-    const uint2 ent_a = make_uint2((uint32_t)(b0 + tid), far_a);
-    const uint2 ent_b = make_uint2((uint32_t)(tid == 0 ? b0 - 1 : b1), far_b);
-    if (has_a)
-    {
-        if (fits) p.pending[s_pending_base + idx_a] = ent_a;
-        else global_climb<kScene>(p, ent_a.x, ent_a.y);
-    }
-    if (has_b)
-    {
-        if (fits) p.pending[s_pending_base + idx_b] = ent_b;
-        else global_climb<kScene>(p, ent_b.x, ent_b.y);
-    }
-    RR_EMIT_STAMP(5);
 }
 
 // Climbers whose sibling lies outside their window: (split, far bound) identifies the node and its range.
@@ -696,20 +801,24 @@ __global__ void __launch_bounds__(256)
 }
 
 template <bool kScene>
-void launch_emit_fit(cudaStream_t s, const EmitParams& p)
+int launch_emit_fit(const DeviceInfo& dev, cudaStream_t s, const EmitParams& p)
 {
-    static bool attr_set = false;
-    if (!attr_set)
+    const uint32_t groups = (p.n + 31) / 32, windows = (p.n + kEmitWindow - 1) / kEmitWindow;
+    const uint32_t ctas   = std::min<uint32_t>((groups + 7) / 8, (uint32_t)dev.sm_count * 8u);
+    static const int occ = [] { const char* e = std::getenv("RR_EMIT_OCC"); return e ? std::atoi(e) : 3; }();
+    switch (occ)
     {
-        RR_CUDA_CHECK(cudaFuncSetAttribute(k_emit_fit<kScene>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem)));
-        attr_set = true;
+    case 4: k_emit_leaves<kScene, 4><<<ctas, 256, 0, s>>>(p); break;
+    case 5: k_emit_leaves<kScene, 5><<<ctas, 256, 0, s>>>(p); break;
+    case 6: k_emit_leaves<kScene, 6><<<ctas, 256, 0, s>>>(p); break;
+    default: k_emit_leaves<kScene, 3><<<ctas, 256, 0, s>>>(p); break;
     }
-    k_emit_fit<kScene><<<(p.n + kEmitLeaves - 1) / kEmitLeaves, kEmitLeaves, sizeof(EmitSmem), s>>>(p);
-    if (p.n > (uint32_t)kEmitLeaves)
-    {
-        const uint32_t threads = std::min<uint32_t>(p.pending_capacity, 148u * 16u * 128u);
-        k_emit_global<kScene><<<(threads + 127) / 128, 128, 0, s>>>(p);
-    }
+    if (p.n <= 32) return 1;  // the whole tree was inside one group
+    k_emit_window<kScene><<<(windows + kWindowWarps - 1) / kWindowWarps, 32 * kWindowWarps, 0, s>>>(p);
+    if (p.n <= (uint32_t)kEmitWindow) return 2;
+    const uint32_t threads = std::min<uint32_t>(p.pending_capacity, 148u * 16u * 128u);
+    k_emit_global<kScene><<<(threads + 127) / 128, 128, 0, s>>>(p);
+    return 3;
 }
 
 inline int grid_for(const DeviceInfo& dev, uint32_t n, int threads, int ctas_per_sm)
@@ -727,7 +836,7 @@ inline int grid_for(const DeviceInfo& dev, uint32_t n, int threads, int ctas_per
 // identities of the ordered encoding; g_aabb[0..2]=min, [4..6]=max as in the reference's uint[8].
 // Hand-over list between k_emit_fit and k_emit_global: ~2 log2(window) entries per 512-leaf window in practice
 // (1 % of n); n/4 leaves a wide margin and a full list only makes the CTA finish its climbs itself.
-static uint32_t emit_pending_capacity(uint32_t n) { return n <= (uint32_t)kEmitLeaves ? 0u : std::max<uint32_t>(1024u, n / 4); }
+static uint32_t emit_pending_capacity(uint32_t n) { return n <= (uint32_t)kEmitWindow ? 0u : std::max<uint32_t>(1024u, n / 4); }
 
 BlasLayout blas_layout(uint32_t n, bool restructure)
 {
@@ -784,11 +893,8 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
     p.codes = sorted_codes; p.refs = sorted_refs; p.n = n; p.flags = flags; p.nodes = nodes; p.mesh = mesh;
     p.pending_count = g_aabb + 7;  // spare word of the scene-AABB block, zeroed with the max half
     p.pending = reinterpret_cast<uint2*>(sc + L.pending_off); p.pending_capacity = L.pending_capacity;
-#ifdef RR_EMIT_TIMELINE
-    p.timeline = reinterpret_cast<unsigned long long*>(sc + L.sort_off + L.sort.tmp_vals_off);  // dead after the sort
-#endif
-    launch_emit_fit<false>(s, p);
-    *dev.launches += n > (uint32_t)kEmitLeaves ? 2 : 1;
+    p.masks = reinterpret_cast<uint32_t*>(sc + L.sort_off + L.sort.tmp_vals_off);  // the sort's ping-pong buffer is dead now
+    *dev.launches += launch_emit_fit<false>(dev, s, p);
     RR_CUDA_CHECK(cudaGetLastError());
     if (restructure) restructure_blas(dev, s, nodes, n, scratch);
 }
@@ -890,8 +996,8 @@ void build_scene(const DeviceInfo& dev, cudaStream_t s, const InstanceDesc* host
     p.fwd     = reinterpret_cast<float4*>(out + L.fwd_off);
     p.pending_count = g_aabb + 7;
     p.pending = reinterpret_cast<uint2*>(sc + L.pending_off); p.pending_capacity = L.pending_capacity;
-    launch_emit_fit<true>(s, p);
-    *dev.launches += n > (uint32_t)kEmitLeaves ? 2 : 1;
+    p.masks = reinterpret_cast<uint32_t*>(sc + L.sort_off + L.sort.tmp_vals_off);  // the sort's ping-pong buffer is dead now
+    *dev.launches += launch_emit_fit<true>(dev, s, p);
     RR_CUDA_CHECK(cudaGetLastError());
 }
 
