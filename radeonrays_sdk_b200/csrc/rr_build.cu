@@ -363,6 +363,7 @@ struct MergeOut
 // One group of up to 32 consecutive top-level subtrees ("elements": sorted leaves [a,b], node id, box), one per lane;
 // D = delta(b, b+1), DL0 = delta left of the first element.  Forms every node whose range lies inside the group and
 // writes its 64 bytes (parent word included when the parent is formed here as well, else INVALID).
+template <bool kLeaves>  // elements are the single leaves a = b = a0 + lane, id = leaf0 + a (saves four shuffles)
 __device__ __forceinline__ MergeOut group_merge(Node* __restrict__ nodes, int n, int cnt, bool valid, int a, int b, uint32_t id, float3 lo,
                                                 float3 hi, int D, int DL0)
 {
@@ -388,8 +389,8 @@ __device__ __forceinline__ MergeOut group_merge(Node* __restrict__ nodes, int n,
     const bool     formed = lane + 1 < cnt && (lmask != 0 || DL0 < D) && rmask != 0;
     const uint32_t IG = __ballot_sync(full, formed);
     const int      Ll = pl + 1;
-    const int      aL = __shfl_sync(full, a, Ll & 31);
-    const int      bR = __shfl_sync(full, b, pr);
+    const int      aL = kLeaves ? a - lane + Ll : __shfl_sync(full, a, Ll & 31);
+    const int      bR = kLeaves ? a - lane + pr : __shfl_sync(full, b, pr);
     int            Dpl = __shfl_sync(full, D, pl < 0 ? 0 : pl);
     if (pl < 0) Dpl = DL0;
     const int      Dpr = __shfl_sync(full, D, pr);
@@ -399,7 +400,7 @@ __device__ __forceinline__ MergeOut group_merge(Node* __restrict__ nodes, int n,
     const int      q   = nleft ? pr : pl;                         // split lane of the parent
     const bool     parent_in = formed && !is_root && q >= 0 && ((IG >> (q & 31)) & 1u);
     const uint32_t pidx = __shfl_sync(full, idx, parent_in ? q : lane);
-    const uint32_t nid  = __shfl_down_sync(full, id, 1);
+    const uint32_t nid  = kLeaves ? id + 1u : __shfl_down_sync(full, id, 1);
     const uint32_t c0 = (Ll == lane) ? id : (uint32_t)b;          // Karras: left child = split, right child = split + 1
     const uint32_t c1 = (pr == lane + 1) ? nid : (uint32_t)(b + 1);
     float3 loL, hiL, loR, hiR;
@@ -437,31 +438,34 @@ __device__ __forceinline__ int delta_of(uint32_t ca, uint32_t cb, int a)  // del
 }
 
 // ---- level 1: one warp per 32 sorted leaves ---------------------------------------------------------------------------
+// Mesh path: persistent warps with a three-deep software pipeline over their groups -- while group g is merged, the
+// vertex loads of g+1, the index loads of g+2 and the ref/code loads of g+3 are in flight, so the dependent chain
+// ref -> indices -> vertices (three DRAM latencies) never stalls the warp (it was 72 % of the stall samples).
 template <bool kScene, int kMinCtas>
 __global__ void __launch_bounds__(256, kMinCtas) k_emit_leaves(EmitParams p)
 {
     const uint32_t full = 0xffffffffu;
     const int n = (int)p.n, leaf0 = n - 1, lane = threadIdx.x & 31;
     const int ngroups = (n + 31) >> 5, nwarps = gridDim.x * (blockDim.x >> 5);
-    for (int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroups; g += nwarps)
+    const int g0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (kScene)
     {
-        const int  wb = g << 5, j = wb + lane, cnt = min(32, n - wb);
-        const bool valid = j < n;
-        // deltas (0 outside the array: smaller than every real delta, 30-bit codes have clz >= 2)
-        const uint32_t c  = valid ? p.codes[j] : 0u;
-        uint32_t       cn = __shfl_down_sync(full, c, 1);
-        if (lane == 31 && j + 1 < n) cn = p.codes[j + 1];
-        const int D = (valid && j + 1 < n) ? delta_of(c, cn, j) : 0;
-        int       DL0 = (lane == 0 && wb > 0) ? delta_of(p.codes[wb - 1], c, wb - 1) : 0;
-        DL0 = __shfl_sync(full, DL0, 0);
-        // gather the leaf
-        float3   lo = make_float3(0.f, 0.f, 0.f), hi = lo;
-        float4   q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
-        if (valid)
+        for (int g = g0; g < ngroups; g += nwarps)
         {
-            const uint32_t ref = p.refs[j];
-            if (kScene)
+            const int  wb = g << 5, j = wb + lane, cnt = min(32, n - wb);
+            const bool valid = j < n;
+            // deltas (0 outside the array: smaller than every real delta, 30-bit codes have clz >= 2)
+            const uint32_t c  = valid ? p.codes[j] : 0u;
+            uint32_t       cn = __shfl_down_sync(full, c, 1);
+            if (lane == 31 && j + 1 < n) cn = p.codes[j + 1];
+            const int D = (valid && j + 1 < n) ? delta_of(c, cn, j) : 0;
+            int       DL0 = (lane == 0 && wb > 0) ? delta_of(p.codes[wb - 1], c, wb - 1) : 0;
+            DL0 = __shfl_sync(full, DL0, 0);
+            float3 lo = make_float3(0.f, 0.f, 0.f), hi = lo;
+            uint32_t ref = 0;
+            if (valid)
             {   // lbvh_fit_aabb_scene.comp:113-130
+                ref = p.refs[j];
                 const float4 bmin = p.boxes[2 * (size_t)ref], bmax = p.boxes[2 * (size_t)ref + 1];
                 lo = xyz(bmin);
                 hi = xyz(bmax);
@@ -474,24 +478,90 @@ __global__ void __launch_bounds__(256, kMinCtas) k_emit_leaves(EmitParams p)
                 p.fwd[3 * (size_t)ref + 0] = make_float4(d.m[0], d.m[1], d.m[2], d.m[3]);
                 p.fwd[3 * (size_t)ref + 1] = make_float4(d.m[4], d.m[5], d.m[6], d.m[7]);
                 p.fwd[3 * (size_t)ref + 2] = make_float4(d.m[8], d.m[9], d.m[10], d.m[11]);
-                q0 = pack(lo, kInvalid); q1 = pack(hi, ref); q2 = pack(lo, kInvalid); q3 = pack(hi, 0u);
             }
-            else
-            {   // lbvh_fit_aabb_mesh.comp:139-163
-                const uint32_t i0 = p.mesh.indices[3 * (size_t)ref + 0], i1 = p.mesh.indices[3 * (size_t)ref + 1],
-                               i2 = p.mesh.indices[3 * (size_t)ref + 2];
-                const float3 v0 = ld3(p.mesh.vertices + (size_t)i0 * p.mesh.stride_floats);
-                const float3 v1 = ld3(p.mesh.vertices + (size_t)i1 * p.mesh.stride_floats);
-                const float3 v2 = ld3(p.mesh.vertices + (size_t)i2 * p.mesh.stride_floats);
-                lo = min3(min3(v0, v1), v2);
-                hi = max3(max3(v0, v1), v2);
-                q0 = pack(v0, kInvalid); q1 = pack(v1, ref); q2 = pack(v2, kInvalid);
-            }
+            const MergeOut o = group_merge<true>(p.nodes, n, cnt, valid, j, j, (uint32_t)(leaf0 + j), lo, hi, D, DL0);
+            if (valid) st_node(p.nodes + leaf0 + j, pack(lo, kInvalid), pack(hi, ref), pack(lo, o.e_parent), pack(hi, 0u));
+            const uint32_t mask = __ballot_sync(full, o.e_over) | __reduce_or_sync(full, o.n_over ? 1u << ((o.n_a - wb) & 31) : 0u);
+            if (lane == 0) p.masks[g] = mask;
         }
-        const MergeOut o = group_merge(p.nodes, n, cnt, valid, j, j, (uint32_t)(leaf0 + j), lo, hi, D, DL0);
-        if (valid) st_node(p.nodes + leaf0 + j, q0, q1, make_float4(q2.x, q2.y, q2.z, __uint_as_float(o.e_parent)), q3);
+        return;
+    }
+    if (g0 >= ngroups) return;
+    const float*    verts   = p.mesh.vertices;
+    const uint32_t* indices = p.mesh.indices;
+    const size_t    vstride = p.mesh.stride_floats;
+    // loads of a group that may lie past the end are clamped to the last leaf (results unused)
+    auto leaf_of = [&](int g) -> int { return min((g << 5) + lane, n - 1); };
+    struct Codes { uint32_t c, edge; };  // own code; lane 0: code left of the group, lane 31: code right of it
+    auto load_codes = [&](int g) -> Codes {
+        const int wb = g << 5;
+        Codes k;
+        k.c    = p.codes[leaf_of(g)];
+        k.edge = 0u;
+        if (lane == 0 && wb > 0 && wb < n) k.edge = p.codes[wb - 1];
+        if (lane == 31 && wb + 32 < n) k.edge = p.codes[wb + 32];
+        return k;
+    };
+    struct Idx { uint32_t i0, i1, i2; };
+    auto load_idx = [&](uint32_t ref) -> Idx {
+        const uint32_t* ip = indices + 3 * (size_t)ref;
+        return Idx{ip[0], ip[1], ip[2]};
+    };
+    struct Tri { float3 v0, v1, v2; };
+    // a vertex as one 8-byte and one 4-byte load (its 12 bytes start at a multiple of 4: either half may be the aligned one)
+    const bool base8 = (reinterpret_cast<uintptr_t>(verts) & 7u) == 0;
+    auto ld_vertex = [&](uint32_t i) -> float3 {
+        const size_t off = (size_t)i * vstride;
+        if (!base8) return ld3(verts + off);
+        const bool   even = (off & 1) == 0;
+        const float2 w = *reinterpret_cast<const float2*>(verts + off + (even ? 0 : 1));
+        const float  u = verts[off + (even ? 2 : 0)];
+        return even ? make_float3(w.x, w.y, u) : make_float3(u, w.x, w.y);
+    };
+    auto load_tri = [&](const Idx& i) -> Tri { return Tri{ld_vertex(i.i0), ld_vertex(i.i1), ld_vertex(i.i2)}; };
+    // prologue
+    uint32_t ref_c = p.refs[leaf_of(g0)];
+    Codes    cod_c = load_codes(g0);
+    uint32_t ref_1 = p.refs[leaf_of(g0 + nwarps)];
+    Codes    cod_1 = load_codes(g0 + nwarps);
+    uint32_t ref_2 = p.refs[leaf_of(g0 + 2 * nwarps)];
+    Tri      tri_c = load_tri(load_idx(ref_c));
+    Idx      idx_1 = load_idx(ref_1);
+    for (int g = g0; g < ngroups; g += nwarps)
+    {
+        // prefetch: vertices of the next group, indices of the one after, ref / codes of the third
+        const Tri      tri_1 = load_tri(idx_1);
+        const Idx      idx_2 = load_idx(ref_2);
+        const uint32_t ref_3 = p.refs[leaf_of(g + 3 * nwarps)];
+        const Codes    cod_2 = load_codes(g + 2 * nwarps);
+
+        const int  wb = g << 5, j = wb + lane, cnt = min(32, n - wb);
+        const bool valid = j < n;
+        // deltas (0 outside the array: smaller than every real delta, 30-bit codes have clz >= 2)
+        uint32_t cn = __shfl_down_sync(full, cod_c.c, 1);
+        if (lane == 31) cn = cod_c.edge;
+        const int D = (valid && j + 1 < n) ? delta_of(cod_c.c, cn, j) : 0;
+        int       DL0 = (lane == 0 && wb > 0) ? delta_of(cod_c.edge, cod_c.c, wb - 1) : 0;
+        DL0 = __shfl_sync(full, DL0, 0);
+        // lbvh_fit_aabb_mesh.comp:139-163
+        const float3 lo = min3(min3(tri_c.v0, tri_c.v1), tri_c.v2), hi = max3(max3(tri_c.v0, tri_c.v1), tri_c.v2);
+        const float3 v2 = tri_c.v2;
+        if (valid)
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p.nodes + leaf0 + j), "f"(tri_c.v0.x),
+                         "f"(tri_c.v0.y), "f"(tri_c.v0.z), "f"(__uint_as_float(kInvalid)), "f"(tri_c.v1.x), "f"(tri_c.v1.y), "f"(tri_c.v1.z),
+                         "f"(__uint_as_float(ref_c))
+                         : "memory");
+        const MergeOut o = group_merge<true>(p.nodes, n, cnt, valid, j, j, (uint32_t)(leaf0 + j), lo, hi, D, DL0);
+        if (valid)
+            asm volatile("st.global.v8.f32 [%0+32], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p.nodes + leaf0 + j), "f"(v2.x), "f"(v2.y),
+                         "f"(v2.z), "f"(__uint_as_float(o.e_parent)), "f"(0.f), "f"(0.f), "f"(0.f), "f"(0.f)
+                         : "memory");
         const uint32_t mask = __ballot_sync(full, o.e_over) | __reduce_or_sync(full, o.n_over ? 1u << ((o.n_a - wb) & 31) : 0u);
         if (lane == 0) p.masks[g] = mask;
+        // rotate the pipeline
+        tri_c = tri_1; ref_c = ref_1; cod_c = cod_1;
+        idx_1 = idx_2; ref_1 = ref_2; cod_1 = cod_2;
+        ref_2 = ref_3;
     }
 }
 
@@ -592,7 +662,7 @@ __global__ void __launch_bounds__(32 * kWindowWarps) k_emit_window(EmitParams p)
                 node_box_ldcg<kScene>(p.nodes, id, leaf0, elo, ehi);
             }
             const int a_first = __shfl_sync(full, a, 0);
-            const MergeOut o = group_merge(p.nodes, n, e1 - e0, v, a, b, id, elo, ehi, v ? delta_adj(b) : 0, delta_adj(a_first - 1));
+            const MergeOut o = group_merge<false>(p.nodes, n, e1 - e0, v, a, b, id, elo, ehi, v ? delta_adj(b) : 0, delta_adj(a_first - 1));
             if (v && o.e_parent != kInvalid) reinterpret_cast<uint32_t*>(p.nodes + id)[11] = o.e_parent;  // q2.w
             if (o.e_over) atomicOr(&s_mask[wi][cur ^ 1][(a - b0) >> 5], 1u << ((a - b0) & 31));
             if (o.n_over) atomicOr(&s_mask[wi][cur ^ 1][(o.n_a - b0) >> 5], 1u << ((o.n_a - b0) & 31));
@@ -804,10 +874,13 @@ template <bool kScene>
 int launch_emit_fit(const DeviceInfo& dev, cudaStream_t s, const EmitParams& p)
 {
     const uint32_t groups = (p.n + 31) / 32, windows = (p.n + kEmitWindow - 1) / kEmitWindow;
-    const uint32_t ctas   = std::min<uint32_t>((groups + 7) / 8, (uint32_t)dev.sm_count * 8u);
-    static const int occ = [] { const char* e = std::getenv("RR_EMIT_OCC"); return e ? std::atoi(e) : 3; }();
+    // persistent warps: exactly the resident CTAs, so that every warp streams through a long run of groups
+    static const int occ = [] { const char* e = std::getenv("RR_EMIT_OCC"); const int v = e ? std::atoi(e) : 3; return v < 2 || v > 6 ? 3 : v; }();
+    static const int per_sm = [] { const char* e = std::getenv("RR_EMIT_GRID"); const int v = e ? std::atoi(e) : 0; return v; }();
+    const uint32_t ctas = std::min<uint32_t>((groups + 7) / 8, (uint32_t)(dev.sm_count * (per_sm > 0 ? per_sm : occ)));
     switch (occ)
     {
+    case 2: k_emit_leaves<kScene, 2><<<ctas, 256, 0, s>>>(p); break;
     case 4: k_emit_leaves<kScene, 4><<<ctas, 256, 0, s>>>(p); break;
     case 5: k_emit_leaves<kScene, 5><<<ctas, 256, 0, s>>>(p); break;
     case 6: k_emit_leaves<kScene, 6><<<ctas, 256, 0, s>>>(p); break;
