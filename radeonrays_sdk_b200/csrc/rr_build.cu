@@ -29,6 +29,17 @@ __device__ __forceinline__ uint32_t float_to_ordered(float f)
 __device__ __forceinline__ float ordered_to_float(uint32_t v) { return __uint_as_float(v ^ (((v >> 31) - 1u) | 0x80000000u)); }
 
 __device__ __forceinline__ float3 ld3(const float* p) { return make_float3(p[0], p[1], p[2]); }
+// A vertex as one 8-byte and one 4-byte load: its 12 bytes start at a multiple of 4, so either half may be the aligned
+// one (base8: the vertex buffer itself is 8-byte aligned).  Two L1 requests instead of three; pays where lanes gather
+// scattered vertices (k_emit_leaves), not in the sweeps over triangles in input order (measured 30 % slower there).
+__device__ __forceinline__ float3 ld_vertex(const float* verts, size_t off, bool base8)
+{
+    if (!base8) return ld3(verts + off);
+    const bool   even = (off & 1) == 0;
+    const float2 w = *reinterpret_cast<const float2*>(verts + off + (even ? 0 : 1));
+    const float  u = verts[off + (even ? 2 : 0)];
+    return even ? make_float3(w.x, w.y, u) : make_float3(u, w.x, w.y);
+}
 __device__ __forceinline__ float3 min3(float3 a, float3 b) { return make_float3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
 __device__ __forceinline__ float3 max3(float3 a, float3 b) { return make_float3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
 __device__ __forceinline__ float3 xyz(float4 q) { return make_float3(q.x, q.y, q.z); }
@@ -508,17 +519,11 @@ __global__ void __launch_bounds__(256, kMinCtas) k_emit_leaves(EmitParams p)
         return Idx{ip[0], ip[1], ip[2]};
     };
     struct Tri { float3 v0, v1, v2; };
-    // a vertex as one 8-byte and one 4-byte load (its 12 bytes start at a multiple of 4: either half may be the aligned one)
     const bool base8 = (reinterpret_cast<uintptr_t>(verts) & 7u) == 0;
-    auto ld_vertex = [&](uint32_t i) -> float3 {
-        const size_t off = (size_t)i * vstride;
-        if (!base8) return ld3(verts + off);
-        const bool   even = (off & 1) == 0;
-        const float2 w = *reinterpret_cast<const float2*>(verts + off + (even ? 0 : 1));
-        const float  u = verts[off + (even ? 2 : 0)];
-        return even ? make_float3(w.x, w.y, u) : make_float3(u, w.x, w.y);
+    auto load_tri = [&](const Idx& i) -> Tri {
+        return Tri{ld_vertex(verts, (size_t)i.i0 * vstride, base8), ld_vertex(verts, (size_t)i.i1 * vstride, base8),
+                   ld_vertex(verts, (size_t)i.i2 * vstride, base8)};
     };
-    auto load_tri = [&](const Idx& i) -> Tri { return Tri{ld_vertex(i.i0), ld_vertex(i.i1), ld_vertex(i.i2)}; };
     // prologue
     uint32_t ref_c = p.refs[leaf_of(g0)];
     Codes    cod_c = load_codes(g0);
@@ -591,7 +596,7 @@ __device__ __forceinline__ void node_box_ldcg(const Node* nodes, uint32_t node, 
 // ---- level 2: one warp per 512-leaf window, over what its 16 groups left over --------------------------------------------
 constexpr int kWindowWarps = 8;  // per CTA
 template <bool kScene>
-__global__ void __launch_bounds__(32 * kWindowWarps) k_emit_window(EmitParams p)
+__global__ void __launch_bounds__(32 * kWindowWarps, 5) k_emit_window(EmitParams p)
 {
     __shared__ uint8_t  s_delta[kWindowWarps][kEmitWindow + 8];  // delta(a, a+1) for a = b0-1 .. b1
     __shared__ uint32_t s_mask[kWindowWarps][2][kEmitWindow / 32];
