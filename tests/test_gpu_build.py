@@ -45,6 +45,59 @@ def test_small_random_meshes(engine, n):
     _check_build(engine, pos, idx)
 
 
+@pytest.mark.parametrize("n", [511, 512, 513, 544, 1023, 1025, 4097, 20000])
+def test_sizes_around_group_and_window_borders(engine, n):
+    """k_emit_leaves works on 32-leaf groups, k_emit_window on 512-leaf windows: sizes on either side of both."""
+    rng = np.random.default_rng(n)
+    pos = rng.random((n + 2, 3), dtype=np.float32)
+    idx = np.stack([np.arange(n), np.arange(n) + 1, np.arange(n) + 2], 1).astype(np.uint32)
+    _check_build(engine, pos, idx)
+
+
+def _clustered_mesh(sizes, seed):
+    """Tiny triangles in clusters that share a Morton cell: runs of equal codes of the given lengths (index tie-break
+    subtrees, some longer than a 512-leaf window) next to isolated triangles -- deep, unbalanced hierarchies."""
+    rng = np.random.default_rng(seed)
+    centres = rng.random((len(sizes), 3)).astype(np.float32)
+    pos, idx = [], []
+    for c, k in zip(centres, sizes):
+        for _ in range(k):
+            b = len(pos)
+            d = (rng.random((3, 3)).astype(np.float32) - np.float32(0.5)) * np.float32(1e-5)
+            pos.extend((c + d).astype(np.float32))
+            idx.append((b, b + 1, b + 2))
+    pos.append(np.zeros(3, np.float32)); pos.append(np.ones(3, np.float32))     # pin the scene box
+    idx.append((len(pos) - 2, len(pos) - 1, len(pos) - 2))
+    return np.asarray(pos, np.float32), np.asarray(idx, np.uint32)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_clustered_codes_deep_hierarchy(engine, seed):
+    rng = np.random.default_rng(100 + seed)
+    sizes = [1, 1, 2, 3, 5, 8, 40, 100, 700, 1500, 33, 31, 32, 1, 513] + list(rng.integers(1, 60, 80))
+    pos, idx = _clustered_mesh(sizes, seed)
+    _check_build(engine, pos, idx)
+    _check_build(engine, pos, idx, flags=0)
+
+
+def test_octree_corner_chain(engine):
+    """One triangle per octree level along the diagonal: the radix tree is a chain (depth ~ code bits), the case in which
+    a group or window merges one node per pass."""
+    pos, idx = [], []
+    for lvl in range(1, 11):
+        for rep in range(3 * lvl):                      # a few per level, spread so codes differ in the low bits
+            c = np.float32(2.0 ** -lvl) * (np.float32(1.0) + np.float32(0.3) * np.float32(rep) / np.float32(3 * lvl))
+            b = len(pos)
+            pos.extend([np.array([c, c, c], np.float32), np.array([c, c, c], np.float32) * np.float32(1.0001), np.array([c, c * np.float32(1.0002), c], np.float32)])
+            idx.append((b, b + 1, b + 2))
+    pos.append(np.zeros(3, np.float32)); pos.append(np.ones(3, np.float32))
+    idx.append((len(pos) - 2, len(pos) - 1, len(pos) - 2))
+    pos, idx = np.asarray(pos, np.float32), np.asarray(idx, np.uint32)
+    _check_build(engine, pos, idx)
+    reps = np.tile(idx, (40, 1))                        # the same chain with every code repeated 40 times (6 640 triangles)
+    _check_build(engine, pos, reps)
+
+
 def test_cornell_box(engine, cornell):
     pos, idx, _ = cornell
     _check_build(engine, pos, idx)
