@@ -196,11 +196,8 @@ struct EmitParams
     const uint32_t* codes;   // sorted
     const uint32_t* refs;    // sorted primitive / instance ids
     uint32_t        n;
-    uint32_t*       flags;   // [n-1], preset to 0xFFFFFFFF: rendezvous word per split position
     Node*           nodes;
-    uint32_t*       pending_count;     // preset to 0: climbers handed from the local to the global kernel
-    uint2*          pending;           // [pending_capacity] (split position, far bound) of each
-    uint32_t        pending_capacity;
+    uint32_t*       lists;   // per 512-leaf window: count + up to kListSlots left ends of the subtrees k_emit_window left over
     uint32_t*       masks;             // [ceil(n/32)] per 32 leaves: left ends of the subtrees k_emit_leaves left over
     // mesh leaves
     MeshDesc mesh;
@@ -272,59 +269,11 @@ __device__ __forceinline__ void affine_inverse(const float* m, float4& r0, float
 // CTA windows with shared-memory images and an atomic climb; barrier-paced rounds; ...): all were bound by the serial
 // gather -> climb -> flush chain of a CTA at 1 536 resident threads per SM.
 constexpr int      kEmitWindow    = 512;  // leaves per k_emit_window warp
-constexpr int      kEmitMaxPasses = 64;
-
-// The rendezvous protocol on the global words, for a node that is already in memory.  (split, far) identify it: the
-// climber covers [far, split] if it is a left child (far <= split), else [split+1, far].
-template <bool kScene>
-__device__ void global_climb(const EmitParams& p, uint32_t split, uint32_t far)
-{
-    const uint32_t n = p.n, leaf0 = n - 1;
-    bool     is_left = far <= split;
-    uint32_t l = is_left ? far : split + 1, r = is_left ? split : far;
-    uint32_t me = (l == r) ? leaf0 + l : (is_left ? r : l);
-    float3   lo, hi;
-    {
-        const float4* mp = reinterpret_cast<const float4*>(p.nodes + me);
-        const float4 m0 = __ldcg(mp), m1 = __ldcg(mp + 1), m2 = __ldcg(mp + 2), m3 = __ldcg(mp + 3);
-        node_box(m0, m1, m2, m3, !kScene && me >= leaf0, lo, hi);
-    }
-    while (true)
-    {
-        __threadfence();  // publish my node before announcing arrival
-        const uint32_t other = atomicExch(&p.flags[split], is_left ? l : r);
-        if (other == kInvalid) break;  // first to arrive: the sibling's climber finishes the parent
-        __threadfence();
-        uint32_t sib, L, R;
-        if (is_left) { L = l; R = other; sib = (split + 1 == R) ? leaf0 + split + 1 : split + 1; }
-        else { L = other; R = r; sib = (L == split) ? leaf0 + split : split; }
-        const float4* sp = reinterpret_cast<const float4*>(p.nodes + sib);
-        const float4 s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2), s3 = __ldcg(sp + 3);
-        float3 slo, shi;
-        node_box(s0, s1, s2, s3, !kScene && sib >= leaf0, slo, shi);
-        const bool is_root        = (L == 0 && R == n - 1);
-        const bool parent_is_left = !is_root && ((L == 0) || (R != n - 1 && delta_adjacent(p.codes, R) > delta_adjacent(p.codes, L - 1)));
-        const uint32_t parent = is_root ? 0u : (parent_is_left ? R : L);
-        float4* pn = reinterpret_cast<float4*>(p.nodes + parent);
-        if (is_left)
-        {
-            pn[0] = pack(lo, me); pn[1] = pack(hi, sib); pn[2] = pack(slo, kInvalid); pn[3] = pack(shi, 0u);
-        }
-        else
-        {
-            pn[0] = pack(slo, sib); pn[1] = pack(shi, me); pn[2] = pack(lo, kInvalid); pn[3] = pack(hi, 0u);
-        }
-        reinterpret_cast<uint32_t*>(p.nodes + me)[11]  = parent;  // q2.w = parent
-        reinterpret_cast<uint32_t*>(p.nodes + sib)[11] = parent;
-        lo = min3(lo, slo);
-        hi = max3(hi, shi);
-        l = L; r = R; me = parent;
-        if (is_root) break;  // its parent word is already INVALID
-        is_left = parent_is_left;
-        split   = is_left ? r : l - 1;
-    }
-}
-
+constexpr int      kEmitMaxPasses = 1100;  // a run of 512 elements needs at most 511 merges, one every other pass
+// What a contiguous run of leaves cannot merge internally are its maximal subtrees: at most two per level of the tree
+// (one on each border path), and a radix tree over 30-bit codes with 32-bit index tie-breaks is at most 62 levels deep.
+constexpr int      kListSlots  = 128;
+constexpr int      kListStride = kListSlots + 1;  // count, then the left ends (sorted leaf indices), ascending
 
 // A whole 64-byte node as two 32-byte stores (STG.E.256): every lane writes full sectors.
 __device__ __forceinline__ void st_node(Node* dst, float4 q0, float4 q1, float4 q2, float4 q3)
@@ -367,7 +316,8 @@ struct MergeOut
     bool     e_over;      // this lane's element is still a top-level subtree (its parent is not formed here, it is not the root)
     uint32_t e_parent;    // its parent's index when that was formed here, else INVALID
     bool     n_over;      // the node this lane formed is a top-level subtree ...
-    int      n_a;         // ... starting at this sorted leaf
+    int      n_a;         // ... starting at this sorted leaf,
+    int      n_lane;      // which is the first leaf of this lane's element
     bool     any_formed;  // warp-uniform
 };
 
@@ -439,6 +389,7 @@ __device__ __forceinline__ MergeOut group_merge(StoreNode&& store_node, int n, i
     o.e_over     = valid && !e_parent_in && !(a == 0 && b == n - 1);
     o.n_over     = formed && !parent_in && !is_root;
     o.n_a        = aL;
+    o.n_lane     = Ll;
     o.any_formed = IG != 0;
     return o;
 }
@@ -684,36 +635,137 @@ __global__ void __launch_bounds__(32 * kWindowWarps, 5) k_emit_window(EmitParams
     }
     if (n <= kEmitWindow) return;  // the whole tree was local
 
-    // ---- hand the subtrees whose sibling lies outside the window to k_emit_global as (split, far bound) ---------------
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(p.pending_count, (uint32_t)M);
-    base = __shfl_sync(full, base, 0);
-    const bool fits = base + (uint32_t)M <= p.pending_capacity;
-    if (!fits) __threadfence();  // list full (it holds n/4 entries; a window hands over ~2 log2(512)): finish the climbs here
-    for (int e0 = 0; e0 < M; e0 += 32)
-    {
-        const int  e = e0 + lane;
-        if (e < M)
-        {
-            const int   a = left_end(e), b = left_end(e + 1) - 1;
-            const bool  is_left = delta_adj(b) > delta_adj(a - 1);
-            const uint2 ent = is_left ? make_uint2((uint32_t)b, (uint32_t)a) : make_uint2((uint32_t)(a - 1), (uint32_t)b);
-            if (fits) p.pending[base + e] = ent;
-            else global_climb<kScene>(p, ent.x, ent.y);
-        }
-    }
+    // ---- what is left has its sibling outside the window: the next level (k_emit_upper) continues from the list of left ends
+    uint32_t* out = p.lists + (size_t)w * kListStride;
+    if (lane == 0) out[0] = (uint32_t)min(M, kListSlots);
+    for (int e = lane; e < min(M, kListSlots); e += 32) out[1 + e] = (uint32_t)left_end(e);
 }
 
-// Climbers whose sibling lies outside their window: (split, far bound) identifies the node and its range.
-template <bool kScene>
-__global__ void __launch_bounds__(128) k_emit_global(EmitParams p)
+// ---- level 3 and above: one CTA per 32 windows of the level below, until one window is the whole tree ----------------------
+// Same passes as k_emit_window, with the groups of a pass spread over the warps of the CTA (a barrier between passes) and
+// the deltas taken from the sorted codes: a few hundred elements per CTA, a few thousand CTAs at the first of these levels
+// for 50 M triangles, one CTA at the last, which forms the root.  No rendezvous words, atomics or fences anywhere in the
+// emission: the build is deterministic down to the order of its memory writes within a node.
+constexpr int kUpperFan      = 32;
+constexpr int kUpperWarps    = 8;
+constexpr int kUpperMaxElems = kUpperFan * kListSlots;
+struct UpperSmem
 {
-    const uint32_t count = min(*p.pending_count, p.pending_capacity);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    uint32_t list[2][kUpperMaxElems + 1];          // left ends of the current elements, ascending; ping-pong
+    uint32_t stage[kUpperMaxElems + 64];           // what each group of a pass leaves over, before compaction
+    uint32_t group_off[kUpperMaxElems / 32 + 4];   // per group: count, then (after the scan) offset
+    uint32_t child_off[kUpperFan + 1];
+};
+
+template <bool kScene>
+__global__ void __launch_bounds__(32 * kUpperWarps) k_emit_upper(EmitParams p, const uint32_t* __restrict__ in_lists, uint32_t num_in,
+                                                                 uint32_t leaves_per_in, uint32_t* __restrict__ out_lists)
+{
+    extern __shared__ __align__(16) unsigned char upper_smem_raw[];
+    UpperSmem& S = *reinterpret_cast<UpperSmem*>(upper_smem_raw);
+    const uint32_t full = 0xffffffffu;
+    const int n = (int)p.n, leaf0 = n - 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t c0 = blockIdx.x * kUpperFan, nc = min((uint32_t)kUpperFan, num_in - c0);
+    const int b1 = (int)min((uint64_t)n, (uint64_t)(c0 + nc) * leaves_per_in) - 1;  // last leaf of this window
+
+    // concatenate the lists of the children
+    if (warp == 0)
     {
-        const uint2 e = p.pending[i];
-        global_climb<kScene>(p, e.x, e.y);
+        const uint32_t c = lane < (int)nc ? in_lists[(size_t)(c0 + lane) * kListStride] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(full, incl, d);
+            if (lane >= d) incl += t;
+        }
+        S.child_off[lane] = incl - c;
+        if (lane == 31) S.child_off[32] = incl;
     }
+    __syncthreads();
+    int M = (int)S.child_off[kUpperFan], cur = 0;
+    for (uint32_t c = warp; c < nc; c += kUpperWarps)
+    {
+        const uint32_t base = S.child_off[c], cn = S.child_off[c + 1] - base;
+        for (uint32_t k = lane; k < cn; k += 32) S.list[0][base + k] = in_lists[(size_t)(c0 + c) * kListStride + 1 + k];
+    }
+    __syncthreads();
+
+    auto delta_at = [&](int a) -> int { return (a >= 0 && a + 1 < n) ? delta_of(p.codes[a], p.codes[a + 1], a) : 0; };
+    auto direct_store = [&](uint32_t idx, float4 q0, float4 q1, float4 q2, float4 q3) { st_node(p.nodes + idx, q0, q1, q2, q3); };
+    bool prev_formed = true;
+    for (int pass = 1; M > 1 && pass < kEmitMaxPasses; ++pass)
+    {
+        const int off = (M > 32 && (pass & 1)) ? 16 : 0;
+        const int ngroups = off ? 1 + (M - 16 + 31) / 32 : (M + 31) / 32;
+        bool any = false;
+        for (int g = warp; g < ngroups; g += kUpperWarps)
+        {
+            const int  e0 = off ? (g == 0 ? 0 : 16 + (g - 1) * 32) : g * 32;
+            const int  e1 = min(M, off && g == 0 ? 16 : e0 + 32);
+            const int  e  = e0 + lane;
+            const bool v  = e < e1;
+            int        a = b1 + 1, b = b1 + 1, D = 0;
+            uint32_t   id = 0;
+            float3     elo = make_float3(0.f, 0.f, 0.f), ehi = elo;
+            if (v)
+            {
+                a = (int)S.list[cur][e];
+                b = e + 1 < M ? (int)S.list[cur][e + 1] - 1 : b1;
+                D = delta_at(b);
+                id = a == b ? (uint32_t)(leaf0 + a) : (uint32_t)(D > delta_at(a - 1) ? b : a);
+                node_box_ldcg<kScene>(p.nodes, id, leaf0, elo, ehi);
+            }
+            const int a_first = __shfl_sync(full, a, 0);
+            const MergeOut o = group_merge<false>(direct_store, n, e1 - e0, v, a, b, id, elo, ehi, D, delta_at(a_first - 1));
+            if (v && o.e_parent != kInvalid) reinterpret_cast<uint32_t*>(p.nodes + id)[11] = o.e_parent;  // q2.w
+            const uint32_t EL = __ballot_sync(full, o.e_over), NL = __ballot_sync(full, o.n_over);
+            const uint32_t below = (1u << lane) - 1u;
+            if (o.e_over) S.stage[32 * g + __popc(EL & below) + __popc(NL & below)] = (uint32_t)a;
+            if (o.n_over)
+            {
+                const uint32_t bl = (1u << o.n_lane) - 1u;
+                S.stage[32 * g + __popc(EL & bl) + __popc(NL & bl)] = (uint32_t)o.n_a;
+            }
+            if (lane == 0) S.group_off[g] = (uint32_t)(__popc(EL) + __popc(NL));
+            any |= o.any_formed;
+        }
+        const bool formed = __syncthreads_or(any) != 0;
+        // compaction: scan the group counts (warp 0), then every thread moves its slot
+        if (warp == 0)
+        {
+            uint32_t run = 0;
+            for (int g0 = 0; g0 < ngroups; g0 += 32)
+            {
+                const uint32_t c = g0 + lane < ngroups ? S.group_off[g0 + lane] : 0u;
+                uint32_t incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1)
+                {
+                    const uint32_t t = __shfl_up_sync(full, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (g0 + lane < ngroups) S.group_off[g0 + lane] = run + incl - c;
+                run += __shfl_sync(full, incl, 31);
+            }
+            if (lane == 0) S.group_off[ngroups] = run;
+        }
+        __syncthreads();
+        for (int t = tid; t < 32 * ngroups; t += 32 * kUpperWarps)
+        {
+            const int g = t >> 5, r = t & 31;
+            const uint32_t base = S.group_off[g];
+            if ((uint32_t)r < S.group_off[g + 1] - base) S.list[cur ^ 1][base + r] = S.stage[t];
+        }
+        M = (int)S.group_off[ngroups];
+        cur ^= 1;
+        __syncthreads();
+        if (ngroups == 1 || (!formed && !prev_formed)) break;
+        prev_formed = formed;
+    }
+    uint32_t* out = out_lists + (size_t)blockIdx.x * kListStride;
+    if (tid == 0) out[0] = (uint32_t)min(M, kListSlots);
+    for (int e = tid; e < min(M, kListSlots); e += 32 * kUpperWarps) out[1 + e] = S.list[cur][e];
 }
 
 // ---- K6: refit / update (lbvh_fit_aabb_mesh.comp with UPDATE_KERNEL, vlk/update_hlbvh.cpp:118-185) ----
@@ -1029,6 +1081,9 @@ __global__ void __launch_bounds__(256)
     reduce_box_to_global(sb, g_aabb);
 }
 
+// Words of the list area one level with `windows` windows needs.
+inline size_t emit_list_words(uint32_t windows) { return align_up((size_t)windows * kListStride, 64); }
+
 template <bool kScene>
 int launch_emit_fit(const DeviceInfo& dev, cudaStream_t s, const EmitParams& p)
 {
@@ -1047,10 +1102,27 @@ int launch_emit_fit(const DeviceInfo& dev, cudaStream_t s, const EmitParams& p)
     }
     if (p.n <= 32) return 1;  // the whole tree was inside one group
     k_emit_window<kScene><<<(windows + kWindowWarps - 1) / kWindowWarps, 32 * kWindowWarps, 0, s>>>(p);
-    if (p.n <= (uint32_t)kEmitWindow) return 2;
-    const uint32_t threads = std::min<uint32_t>(p.pending_capacity, 148u * 16u * 128u);
-    k_emit_global<kScene><<<(threads + 127) / 128, 128, 0, s>>>(p);
-    return 3;
+    int launches = 2;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        RR_CUDA_CHECK(cudaFuncSetAttribute(k_emit_upper<kScene>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpperSmem)));
+        attr_set = true;
+    }
+    // upper levels: 32 windows of the level below per CTA, lists ping-pong between the two halves of the list area
+    uint32_t  num = windows, leaves_per = (uint32_t)kEmitWindow;
+    uint32_t* in  = p.lists;
+    uint32_t* out = p.lists + emit_list_words(windows);
+    while (num > 1)
+    {
+        const uint32_t upper_ctas = (num + kUpperFan - 1) / kUpperFan;
+        k_emit_upper<kScene><<<upper_ctas, 32 * kUpperWarps, sizeof(UpperSmem), s>>>(p, in, num, leaves_per, out);
+        ++launches;
+        num = upper_ctas;
+        leaves_per = (uint32_t)std::min<uint64_t>((uint64_t)leaves_per * kUpperFan, 0x80000000ull);
+        std::swap(in, out);
+    }
+    return launches;
 }
 
 inline int grid_for(const DeviceInfo& dev, uint32_t n, int threads, int ctas_per_sm)
@@ -1062,13 +1134,16 @@ inline int grid_for(const DeviceInfo& dev, uint32_t n, int threads, int ctas_per
 
 // ---- layouts -------------------------------------------------------------------------------------------
 // Build scratch: [aabb_max 16 | sort hist/tickets/status]  <- one memset(0)
-//                [aabb_min 16 | flags 4(N-1)]              <- one memset(0xFF)
+//                [aabb_min 16]                             <- one memset(0xFF)
 //                codes 4N | sorted codes 4N | sorted refs 4N | sort tmp keys/vals 8N
 // The scene-AABB words are split so that each memset node also initialises the min (all ones) / max (zero)
 // identities of the ordered encoding; g_aabb[0..2]=min, [4..6]=max as in the reference's uint[8].
-// Hand-over list between k_emit_fit and k_emit_global: ~2 log2(window) entries per 512-leaf window in practice
-// (1 % of n); n/4 leaves a wide margin and a full list only makes the CTA finish its climbs itself.
-static uint32_t emit_pending_capacity(uint32_t n) { return n <= (uint32_t)kEmitWindow ? 0u : std::max<uint32_t>(1024u, n / 4); }
+// List area of the emission levels: one list per 512-leaf window, and one per window of the next level (ping-pong).
+static size_t emit_list_bytes(uint32_t n)
+{
+    const uint32_t windows = (n + kEmitWindow - 1) / kEmitWindow;
+    return n <= (uint32_t)kEmitWindow ? 0 : sizeof(uint32_t) * (emit_list_words(windows) + emit_list_words((windows + kUpperFan - 1) / kUpperFan));
+}
 
 BlasLayout blas_layout(uint32_t n, bool restructure)
 {
@@ -1079,13 +1154,13 @@ BlasLayout blas_layout(uint32_t n, bool restructure)
     // region A (memset 0xFF): aabb min (16 B) + flags
     L.aabb_off  = off;              // 32 B: min[4] then max[4]
     off += 32;
-    L.flags_off = off; off += align_up(sizeof(uint32_t) * (size_t)(n ? n : 1), 256);
+    L.flags_off = off; off += 256;  // (no rendezvous words any more; keeps the min half of the scene AABB on its own line)
     L.codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sorted_codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sorted_refs_off  = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sort_off = off; off += L.sort.total;
-    L.pending_capacity = emit_pending_capacity(n);
-    L.pending_off = off; off += align_up(sizeof(uint2) * (size_t)L.pending_capacity, 256);
+    L.pending_capacity = 0;
+    L.pending_off = off; off += align_up(emit_list_bytes(n), 256);
     L.treelet_off  = 0;
     L.treelet_size = restructure ? treelet_scratch_size(n) : 0;
     L.scratch_total = std::max(off, L.treelet_size);
@@ -1093,13 +1168,11 @@ BlasLayout blas_layout(uint32_t n, bool restructure)
     return L;
 }
 
-static void reset_build_scratch(cudaStream_t s, char* sc, size_t aabb_off, size_t flags_off, size_t flags_bytes, const SortLayout& sl,
-                                size_t sort_off)
+static void reset_build_scratch(cudaStream_t s, char* sc, size_t aabb_off, const SortLayout& sl, size_t sort_off)
 {
-    // min words + flags -> 0xFF ; max words -> 0 ; sort bookkeeping -> 0
+    // min words -> 0xFF ; max words -> 0 ; sort bookkeeping -> 0
     RR_CUDA_CHECK(cudaMemsetAsync(sc + aabb_off, 0xFF, 16, s));
     RR_CUDA_CHECK(cudaMemsetAsync(sc + aabb_off + 16, 0x00, 16, s));
-    RR_CUDA_CHECK(cudaMemsetAsync(sc + flags_off, 0xFF, flags_bytes, s));
     RR_CUDA_CHECK(cudaMemsetAsync(sc + sort_off + sl.hist_off, 0, sl.tmp_keys_off - sl.hist_off, s));
 }
 
@@ -1110,21 +1183,19 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
     if (n == 0) return;
     char*     sc           = (char*)scratch;
     uint32_t* g_aabb       = reinterpret_cast<uint32_t*>(sc + L.aabb_off);
-    uint32_t* flags        = reinterpret_cast<uint32_t*>(sc + L.flags_off);
     uint32_t* codes        = reinterpret_cast<uint32_t*>(sc + L.codes_off);
     uint32_t* sorted_codes = reinterpret_cast<uint32_t*>(sc + L.sorted_codes_off);
     uint32_t* sorted_refs  = reinterpret_cast<uint32_t*>(sc + L.sorted_refs_off);
     void*     sort_scratch = sc + L.sort_off;
 
-    reset_build_scratch(s, sc, L.aabb_off, L.flags_off, sizeof(uint32_t) * (size_t)n, L.sort, L.sort_off);
+    reset_build_scratch(s, sc, L.aabb_off, L.sort, L.sort_off);
     k_scene_aabb<<<grid_for(dev, n, 256, 8), 256, 0, s>>>(mesh, g_aabb);
     k_morton<false><<<grid_for(dev, n, 256, 8), 256, 0, s>>>(mesh, nullptr, n, g_aabb, codes, sort_hist_ptr(L.sort, sort_scratch));
     *dev.launches += 2;
     sort_pairs(dev, s, L.sort, sort_scratch, codes, nullptr, sorted_codes, sorted_refs);
     EmitParams p{};
-    p.codes = sorted_codes; p.refs = sorted_refs; p.n = n; p.flags = flags; p.nodes = nodes; p.mesh = mesh;
-    p.pending_count = g_aabb + 7;  // spare word of the scene-AABB block, zeroed with the max half
-    p.pending = reinterpret_cast<uint2*>(sc + L.pending_off); p.pending_capacity = L.pending_capacity;
+    p.codes = sorted_codes; p.refs = sorted_refs; p.n = n; p.nodes = nodes; p.mesh = mesh;
+    p.lists = reinterpret_cast<uint32_t*>(sc + L.pending_off);
     p.masks = reinterpret_cast<uint32_t*>(sc + L.sort_off + L.sort.tmp_vals_off);  // the sort's ping-pong buffer is dead now
     *dev.launches += launch_emit_fit<false>(dev, s, p);
     RR_CUDA_CHECK(cudaGetLastError());
@@ -1160,7 +1231,12 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
     L.items_b = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (size_t)cap, 256));
     L.capacity = cap;
     RR_CUDA_CHECK(cudaMemsetAsync(sc, 0, 8, s));
-    k_refit_leaves<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)dev.sm_count * 3u), 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, cap);
+    // stage 1: warp-cooperative persistent kernel for large meshes; below ~1 M triangles its pipeline prologue costs more than
+    // it hides (Sponza: 0.150 against 0.133 ms) and the one-thread-per-leaf version (3 levels) is used
+    if (n >= (1u << 20))
+        k_refit_leaves<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)dev.sm_count * 3u), 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, cap);
+    else
+        k_refit<true><<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n, nullptr, nullptr, 3u, L.count_a, L.items_a, cap);
     const uint32_t grid2 = std::min<uint32_t>((cap + 255) / 256, (uint32_t)dev.sm_count * 64u);
     k_refit<false><<<grid2, 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, 6u, L.count_b, L.items_b, cap);
     const uint32_t grid3 = std::min<uint32_t>((cap / 64 + 255) / 256 + 1, (uint32_t)dev.sm_count * 16u);
@@ -1184,15 +1260,15 @@ SceneLayout scene_layout(uint32_t n)
     L.result_total = off;
     off = 0;
     L.aabb_off  = off; off += 32;
-    L.flags_off = off; off += align_up(sizeof(uint32_t) * (size_t)(n ? n : 1), 256);
+    L.flags_off = off; off += 256;  // (no rendezvous words any more; keeps the min half of the scene AABB on its own line)
     L.desc_off  = off; off += align_up(sizeof(InstanceDesc) * (size_t)n, 256);
     L.boxes_off = off; off += align_up(32 * (size_t)n, 256);
     L.codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sorted_codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sorted_refs_off  = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sort_off = off; off += L.sort.total;
-    L.pending_capacity = emit_pending_capacity(n);
-    L.pending_off = off; off += align_up(sizeof(uint2) * (size_t)L.pending_capacity, 256);
+    L.pending_capacity = 0;
+    L.pending_off = off; off += align_up(emit_list_bytes(n), 256);
     L.scratch_total = off;
     return L;
 }
@@ -1205,7 +1281,6 @@ void build_scene(const DeviceInfo& dev, cudaStream_t s, const InstanceDesc* host
     char* sc = (char*)scratch;
     char* out = (char*)scene;
     uint32_t*     g_aabb       = reinterpret_cast<uint32_t*>(sc + L.aabb_off);
-    uint32_t*     flags        = reinterpret_cast<uint32_t*>(sc + L.flags_off);
     InstanceDesc* descs        = reinterpret_cast<InstanceDesc*>(sc + L.desc_off);
     float4*       boxes        = reinterpret_cast<float4*>(sc + L.boxes_off);
     uint32_t*     codes        = reinterpret_cast<uint32_t*>(sc + L.codes_off);
@@ -1214,20 +1289,19 @@ void build_scene(const DeviceInfo& dev, cudaStream_t s, const InstanceDesc* host
     void*         sort_scratch = sc + L.sort_off;
 
     RR_CUDA_CHECK(cudaMemcpyAsync(descs, host_descs, sizeof(InstanceDesc) * (size_t)n, cudaMemcpyHostToDevice, s));
-    reset_build_scratch(s, sc, L.aabb_off, L.flags_off, sizeof(uint32_t) * (size_t)n, L.sort, L.sort_off);
+    reset_build_scratch(s, sc, L.aabb_off, L.sort, L.sort_off);
     k_instance_boxes<<<grid_for(dev, n, 256, 4), 256, 0, s>>>(descs, n, corner_quirk ? 1 : 0, boxes, g_aabb);
     k_morton<true><<<grid_for(dev, n, 256, 4), 256, 0, s>>>(MeshDesc{}, boxes, n, g_aabb, codes, sort_hist_ptr(L.sort, sort_scratch));
     *dev.launches += 2;
     sort_pairs(dev, s, L.sort, sort_scratch, codes, nullptr, sorted_codes, sorted_refs);
     EmitParams p{};
-    p.codes = sorted_codes; p.refs = sorted_refs; p.n = n; p.flags = flags;
+    p.codes = sorted_codes; p.refs = sorted_refs; p.n = n;
     p.nodes   = reinterpret_cast<Node*>(out + L.nodes_off);
     p.boxes   = boxes;
     p.descs   = descs;
     p.records = reinterpret_cast<InstanceRecord*>(out + L.records_off);
     p.fwd     = reinterpret_cast<float4*>(out + L.fwd_off);
-    p.pending_count = g_aabb + 7;
-    p.pending = reinterpret_cast<uint2*>(sc + L.pending_off); p.pending_capacity = L.pending_capacity;
+    p.lists = reinterpret_cast<uint32_t*>(sc + L.pending_off);
     p.masks = reinterpret_cast<uint32_t*>(sc + L.sort_off + L.sort.tmp_vals_off);  // the sort's ping-pong buffer is dead now
     *dev.launches += launch_emit_fit<true>(dev, s, p);
     RR_CUDA_CHECK(cudaGetLastError());
