@@ -254,20 +254,20 @@ __device__ __forceinline__ void affine_inverse(const float* m, float4& r0, float
 // side -- the range FindSpan/FindSplit find by binary search from the node's own index.  Every subtree that lies inside
 // a run of leaves also has its internal node indices inside that run.
 //
-// B200 mapping (three kernels, no barriers, no shared-memory images):
+// B200 mapping (no rendezvous words, atomics or fences anywhere; no shared-memory node images):
 //   k_emit_leaves -- one warp per 32 consecutive sorted leaves.  group_merge() forms, in closed form and with ballots and
 //     shuffles only, EVERY node whose range lies inside the 32 leaves (~85 % of all internal nodes): range, Karras index,
 //     child ids, parent index, and both child boxes as range min/max over the lanes.  Leaves and nodes go straight to HBM
 //     (64 B per lane, full sectors); what cannot be decided inside the group -- its maximal subtrees -- is recorded as one
-//     32-bit mask of left ends.  Warps are independent, so memory latency of the gather (ref -> indices -> vertices) is
-//     hidden by the other warps of the SM like in any streaming kernel.
+//     32-bit mask of left ends.  Warps are persistent and software-pipeline the gather (ref -> indices -> vertices).
 //   k_emit_window -- one warp per 512-leaf window repeats group_merge() over the left-over subtrees of its 16 groups
-//     (boxes read back from the node images, L2), 32 at a time, until one group holds them all (2-3 passes).
-//   k_emit_global -- the ~2 % of subtrees whose sibling lies outside their window finish with the classic atomic
-//     rendezvous protocol on global words, one thread per subtree.
+//     (boxes read back from the node images, L2), 32 at a time, until one group holds them all (2-3 passes); what is
+//     left (~10 subtrees, at most 124: two per tree level) goes to a per-window list.
+//   k_emit_upper  -- one CTA per 32 windows of the level below, the groups of a pass spread over its warps; launched
+//     level after level (512 -> 16 Ki -> 512 Ki -> ... leaves per window) until one window is the whole tree and the root
+//     is formed.
 // profiles/round1_summary.md lists the variants measured before this one (single kernel with global atomics; 512-leaf
-// CTA windows with shared-memory images and an atomic climb; barrier-paced rounds; ...): all were bound by the serial
-// gather -> climb -> flush chain of a CTA at 1 536 resident threads per SM.
+// CTA windows with shared-memory images and an atomic climb; barrier-paced rounds; a final global atomic climb; ...).
 constexpr int      kEmitWindow    = 512;  // leaves per k_emit_window warp
 constexpr int      kEmitMaxPasses = 1100;  // a run of 512 elements needs at most 511 merges, one every other pass
 // What a contiguous run of leaves cannot merge internally are its maximal subtrees: at most two per level of the tree
@@ -1231,9 +1231,9 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
     L.items_b = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (size_t)cap, 256));
     L.capacity = cap;
     RR_CUDA_CHECK(cudaMemsetAsync(sc, 0, 8, s));
-    // stage 1: warp-cooperative persistent kernel for large meshes; below ~1 M triangles its pipeline prologue costs more than
-    // it hides (Sponza: 0.150 against 0.133 ms) and the one-thread-per-leaf version (3 levels) is used
-    if (n >= (1u << 20))
+    // stage 1: warp-cooperative persistent kernel for large meshes; for small ones its pipeline prologue costs more than it
+    // hides (Sponza, 262 k triangles: 0.150 against 0.133 ms) and the one-thread-per-leaf version (3 levels) is used
+    if (n >= 500000u)
         k_refit_leaves<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)dev.sm_count * 3u), 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, cap);
     else
         k_refit<true><<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n, nullptr, nullptr, 3u, L.count_a, L.items_a, cap);
