@@ -20,4 +20,4 @@ timeout 600 python tools/bench_build.py --sizes 1000x500,4000x1000,5000x5000 --r
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_build50m.csv python tools/bench_build.py --sizes 5000x5000 --reps 1 > gpurun_out/build50m_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:^k_trace$ -s 1 -c 1 -o gpurun_out/prof_trace -f python tools/profile_trace.py --reps 2 > gpurun_out/ncu_trace.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_onesweep|k_emit|k_morton|k_scene_aabb|k_refit' -c 12 -o gpurun_out/prof_build -f python tools/bench_build.py --sizes 4000x1000 --reps 1 > gpurun_out/ncu_build.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_onesweep|k_emit|k_morton|k_scene_aabb|k_refit' -c 24 -o gpurun_out/prof_build -f python tools/bench_build.py --sizes 4000x1000 --reps 1 > gpurun_out/ncu_build.log 2>&1
