@@ -112,6 +112,15 @@ __global__ void __launch_bounds__(kTreeletWarps * 32)
                   const uint32_t* __restrict__ roots)
 {
     __shared__ WarpScratch s_all[kTreeletWarps];
+    // candidate partitions of every subset with 2..5 leaves, in the reference's enumeration order: computed once per CTA
+    // (thread t fills the row of subset t) instead of bit-depositing k+1 for each of the ~700 candidates of every treelet
+    __shared__ uint8_t s_part_table[128][16];
+    {
+        const uint32_t s = threadIdx.x, bits = __popc(s);
+        if (bits >= 2 && bits <= 5)
+            for (uint32_t k = 0; k < (1u << (bits - 1)) - 1u; ++k) s_part_table[s][k] = (uint8_t)partition_k(s, k);
+    }
+    __syncthreads();
     const int      lane  = threadIdx.x & 31;
     const uint32_t w     = blockIdx.x * kTreeletWarps + (threadIdx.x >> 5);
     if (w >= *root_count) return;
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(kTreeletWarps * 32)
                 uint32_t best = 0;
                 for (uint32_t k = 0; k < K; ++k)
                 {
-                    const uint32_t p = partition_k(s, k);
+                    const uint32_t p = s_part_table[s][k];
                     const float    c = S.cost[p] + S.cost[s ^ p];
                     if (best == 0 || c < lowest) { lowest = c; best = p; }
                 }
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(kTreeletWarps * 32)
             uint32_t best_k = 0xFFFFu, best = 0;
             for (uint32_t k = 2 * lane; k < 62u && k < 2u * lane + 2; ++k)
             {
-                const uint32_t p = partition_k(s, k);
+                const uint32_t p = (k + 1u) << 1;  // = partition_k(0x7f, k): k+1 deposited into bits 1..6
                 const float    c = S.cost[p] + S.cost[s ^ p];
                 if (best == 0 || c < lowest) { lowest = c; best = p; best_k = k; }
             }
