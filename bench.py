@@ -33,6 +33,9 @@ LANE_VISITS_PER_RAY = 66.6   # warp-iterations x 32 / rays of the C2 batch on th
 BUILD_BYTES_PER_TRI = 348    # 48 aabb + 48 morton + 4 code + 60 sort + 12 emit reads + 48 gather + 128 nodes
 
 
+BOUND_CPUS = 0
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -112,10 +115,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
+def bind_to_gpu_cpus(local):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, before any pinned host buffer is allocated, so the
+    H2D / D2H copies of the e2e leg do not cross sockets.  Returns how many CPUs the rank may use (0: left unbound)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in range(ncpu) if (mask[c // 64] >> (c % 64)) & 1 and c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def dist_setup(n_gpus):
     import torch
     import torch.distributed as dist
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    global BOUND_CPUS
+    BOUND_CPUS = bind_to_gpu_cpus(local) if world > 1 else 0
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
@@ -241,7 +265,8 @@ def run_ours(args):
                    "rays_per_step_per_gpu": n_rays, "bvh": f"{args.bvh} build", "parallelism": f"ray shards x{world}, BLAS broadcast",
                    "l2": "ray+hit buffers per step (398 MB) exceed the 126 MB L2; the 33.6 MB BVH is meant to stay L2 resident"},
         "e2e": {"value": round(e2e_mrays, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n_rays * world, "d2h_bytes_per_step": 16 * n_rays * world,
-                "ms_per_step": round(ms_e2e, 4), "pipeline": f"{args.e2e_chunks} slices, H2D / rrCmdIntersect / D2H on three streams"},
+                "ms_per_step": round(ms_e2e, 4), "pipeline": f"{args.e2e_chunks} slices, H2D / rrCmdIntersect / D2H on three streams",
+                "cpus_bound_to_gpu": BOUND_CPUS},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": TRACE_DRAM_BYTES_PER_LAUNCH if (n_rays, args.bvh) == (WIDTH * HEIGHT, "quality") else None,

@@ -15,6 +15,7 @@ ap.add_argument("--rays", default="primary")
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--width", type=int, default=3840)
 ap.add_argument("--height", type=int, default=2160)
+ap.add_argument("--presort", default="", help="experiment: reorder the rays on the host first: octant | octant+cell")
 a = ap.parse_args()
 eng = Engine(0)
 ctx = eng.ctx
@@ -25,6 +26,28 @@ if a.rays != "primary":
     prim = W.sponza_primary_rays(1024, 1024)
     hits = eng.intersect(g, prim)
     rays = (W.diffuse_rays if a.rays == "diffuse" else W.shadow_rays)(pos, idx, prim, hits, count=1 << 24)
+if a.presort:
+    f = rays.view(np.float32).reshape(-1, 8)
+    o, d = f[:, 0:3], f[:, 4:7]
+    octant = ((d[:, 0] < 0).astype(np.uint64) | ((d[:, 1] < 0).astype(np.uint64) << 1) | ((d[:, 2] < 0).astype(np.uint64) << 2))
+    key = octant << 40
+    if "cell" in a.presort:
+        lo, hi = pos.min(0), pos.max(0)
+        q = np.clip(((o - lo) / (hi - lo) * 64).astype(np.int64), 0, 63).astype(np.uint64)
+        def spread(v):
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            v = (v | (v << 2)) & 0x09249249
+            return v
+        key |= (spread(q[:, 0]) << 2 | spread(q[:, 1]) << 1 | spread(q[:, 2])) << 8
+    if "dir" in a.presort:
+        dn = d / np.linalg.norm(d, axis=1, keepdims=True)
+        dq = np.clip((np.abs(dn) * 4).astype(np.int64), 0, 3).astype(np.uint64)
+        key |= dq[:, 0] << 4 | dq[:, 1] << 2 | dq[:, 2]
+    order = np.argsort(key, kind="stable")
+    rays = np.ascontiguousarray(rays[order])
+    print("presorted by", a.presort)
 n = rays.shape[0]
 full = a.query == "closest"
 rb = eng.make_ray_buffers(n, api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT if full else api.RR_INTERSECT_QUERY_OUTPUT_INSTANCE_ID)
