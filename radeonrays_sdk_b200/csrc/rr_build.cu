@@ -401,11 +401,12 @@ __device__ __forceinline__ int delta_of(uint32_t ca, uint32_t cb, int a)  // del
 }
 
 // ---- level 1: one warp per 32 sorted leaves ---------------------------------------------------------------------------
+constexpr int kLeavesCtasPerSm = 3;  // 80 registers; 4 / 5 / 6 CTAs per SM measured slower (spills), profiles/round1_summary.md
 // Mesh path: persistent warps with a three-deep software pipeline over their groups -- while group g is merged, the
 // vertex loads of g+1, the index loads of g+2 and the ref/code loads of g+3 are in flight, so the dependent chain
 // ref -> indices -> vertices (three DRAM latencies) never stalls the warp (it was 72 % of the stall samples).
-template <bool kScene, int kMinCtas>
-__global__ void __launch_bounds__(256, kMinCtas) k_emit_leaves(EmitParams p)
+template <bool kScene>
+__global__ void __launch_bounds__(256, kLeavesCtasPerSm) k_emit_leaves(EmitParams p)
 {
     const uint32_t full = 0xffffffffu;
     const int n = (int)p.n, leaf0 = n - 1, lane = threadIdx.x & 31;
@@ -1089,17 +1090,8 @@ int launch_emit_fit(const DeviceInfo& dev, cudaStream_t s, const EmitParams& p)
 {
     const uint32_t groups = (p.n + 31) / 32, windows = (p.n + kEmitWindow - 1) / kEmitWindow;
     // persistent warps: exactly the resident CTAs, so that every warp streams through a long run of groups
-    static const int occ = [] { const char* e = std::getenv("RR_EMIT_OCC"); const int v = e ? std::atoi(e) : 3; return v < 2 || v > 6 ? 3 : v; }();
-    static const int per_sm = [] { const char* e = std::getenv("RR_EMIT_GRID"); const int v = e ? std::atoi(e) : 0; return v; }();
-    const uint32_t ctas = std::min<uint32_t>((groups + 7) / 8, (uint32_t)(dev.sm_count * (per_sm > 0 ? per_sm : occ)));
-    switch (occ)
-    {
-    case 2: k_emit_leaves<kScene, 2><<<ctas, 256, 0, s>>>(p); break;
-    case 4: k_emit_leaves<kScene, 4><<<ctas, 256, 0, s>>>(p); break;
-    case 5: k_emit_leaves<kScene, 5><<<ctas, 256, 0, s>>>(p); break;
-    case 6: k_emit_leaves<kScene, 6><<<ctas, 256, 0, s>>>(p); break;
-    default: k_emit_leaves<kScene, 3><<<ctas, 256, 0, s>>>(p); break;
-    }
+    const uint32_t ctas = std::min<uint32_t>((groups + 7) / 8, (uint32_t)(dev.sm_count * kLeavesCtasPerSm));
+    k_emit_leaves<kScene><<<ctas, 256, 0, s>>>(p);
     if (p.n <= 32) return 1;  // the whole tree was inside one group
     k_emit_window<kScene><<<(windows + kWindowWarps - 1) / kWindowWarps, 32 * kWindowWarps, 0, s>>>(p);
     int launches = 2;
@@ -1151,16 +1143,15 @@ BlasLayout blas_layout(uint32_t n, bool restructure)
     L.n    = n;
     L.sort = sort_layout(n);
     size_t off = 0;
-    // region A (memset 0xFF): aabb min (16 B) + flags
+    // scene AABB: min words preset to 0xFF.., max words to 0
     L.aabb_off  = off;              // 32 B: min[4] then max[4]
     off += 32;
-    L.flags_off = off; off += 256;  // (no rendezvous words any more; keeps the min half of the scene AABB on its own line)
+    off += 256 - 32;  // the scene AABB keeps a 256-byte line of its own
     L.codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sorted_codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sorted_refs_off  = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sort_off = off; off += L.sort.total;
-    L.pending_capacity = 0;
-    L.pending_off = off; off += align_up(emit_list_bytes(n), 256);
+    L.lists_off = off; off += align_up(emit_list_bytes(n), 256);
     L.treelet_off  = 0;
     L.treelet_size = restructure ? treelet_scratch_size(n) : 0;
     L.scratch_total = std::max(off, L.treelet_size);
@@ -1195,7 +1186,7 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
     sort_pairs(dev, s, L.sort, sort_scratch, codes, nullptr, sorted_codes, sorted_refs);
     EmitParams p{};
     p.codes = sorted_codes; p.refs = sorted_refs; p.n = n; p.nodes = nodes; p.mesh = mesh;
-    p.lists = reinterpret_cast<uint32_t*>(sc + L.pending_off);
+    p.lists = reinterpret_cast<uint32_t*>(sc + L.lists_off);
     p.masks = reinterpret_cast<uint32_t*>(sc + L.sort_off + L.sort.tmp_vals_off);  // the sort's ping-pong buffer is dead now
     *dev.launches += launch_emit_fit<false>(dev, s, p);
     RR_CUDA_CHECK(cudaGetLastError());
@@ -1260,15 +1251,14 @@ SceneLayout scene_layout(uint32_t n)
     L.result_total = off;
     off = 0;
     L.aabb_off  = off; off += 32;
-    L.flags_off = off; off += 256;  // (no rendezvous words any more; keeps the min half of the scene AABB on its own line)
+    off += 256 - 32;  // the scene AABB keeps a 256-byte line of its own
     L.desc_off  = off; off += align_up(sizeof(InstanceDesc) * (size_t)n, 256);
     L.boxes_off = off; off += align_up(32 * (size_t)n, 256);
     L.codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sorted_codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sorted_refs_off  = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sort_off = off; off += L.sort.total;
-    L.pending_capacity = 0;
-    L.pending_off = off; off += align_up(emit_list_bytes(n), 256);
+    L.lists_off = off; off += align_up(emit_list_bytes(n), 256);
     L.scratch_total = off;
     return L;
 }
@@ -1301,7 +1291,7 @@ void build_scene(const DeviceInfo& dev, cudaStream_t s, const InstanceDesc* host
     p.descs   = descs;
     p.records = reinterpret_cast<InstanceRecord*>(out + L.records_off);
     p.fwd     = reinterpret_cast<float4*>(out + L.fwd_off);
-    p.lists = reinterpret_cast<uint32_t*>(sc + L.pending_off);
+    p.lists = reinterpret_cast<uint32_t*>(sc + L.lists_off);
     p.masks = reinterpret_cast<uint32_t*>(sc + L.sort_off + L.sort.tmp_vals_off);  // the sort's ping-pong buffer is dead now
     *dev.launches += launch_emit_fit<true>(dev, s, p);
     RR_CUDA_CHECK(cudaGetLastError());

@@ -107,8 +107,7 @@ struct MeshDesc
 struct BlasLayout
 {
     uint32_t   n = 0;
-    size_t     aabb_off = 0, codes_off = 0, sorted_codes_off = 0, sorted_refs_off = 0, flags_off = 0, sort_off = 0, pending_off = 0;
-    uint32_t   pending_capacity = 0;
+    size_t     aabb_off = 0, codes_off = 0, sorted_codes_off = 0, sorted_refs_off = 0, sort_off = 0, lists_off = 0;
     size_t     treelet_off = 0, treelet_size = 0;
     SortLayout sort;
     size_t     scratch_total = 0, result_total = 0;
@@ -125,8 +124,7 @@ struct SceneLayout
     uint32_t   n = 0;
     size_t     nodes_off = 0, records_off = 0, fwd_off = 0, result_total = 0;  // scene buffer
     size_t     desc_off = 0, boxes_off = 0, aabb_off = 0, codes_off = 0, sorted_codes_off = 0, sorted_refs_off = 0,
-               flags_off = 0, sort_off = 0, pending_off = 0, scratch_total = 0;  // temporary buffer
-    uint32_t   pending_capacity = 0;
+               sort_off = 0, lists_off = 0, scratch_total = 0;  // temporary buffer
     SortLayout sort;
 };
 SceneLayout scene_layout(uint32_t instance_count);
