@@ -922,8 +922,6 @@ __global__ void __launch_bounds__(256, 3)
         return Tri{ld_vertex(verts, (size_t)i.i0 * vstride, base8), ld_vertex(verts, (size_t)i.i1 * vstride, base8),
                    ld_vertex(verts, (size_t)i.i2 * vstride, base8)};
     };
-    // appends this warp's finished-but-waiting subtrees to the stage-2 list; a full list (adversarial topologies only) makes
-    // the lane finish its climb here with the parity rendezvous
     // appends this warp's finished-but-waiting subtrees (up to two per lane) to the stage-2 list with one atomic; a full list
     // (adversarial topologies only) makes the lane finish the climb here with the parity rendezvous
     auto climb_here = [&](uint32_t me) {
