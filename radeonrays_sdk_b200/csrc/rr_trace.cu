@@ -31,7 +31,11 @@ namespace rr
 namespace
 {
 constexpr int kTraceThreads = 128;
-constexpr int kSmemStack    = 32;   // entries per thread kept in shared memory
+// entries per thread kept in shared memory: 24 for one-level traces (measured 16 / 20 / 24 / 28 / 32: 5187 / 5470 / 5714 /
+// 5655 / 5545 Mrays/s on Sponza primary rays -- a smaller stack leaves more of the SM's 256 KB to L1, a too small one sends
+// rays to the deep kernel), 32 for two-level traces (TLAS + sentinel + BLAS entries)
+constexpr int kSmemStack1   = 24;
+constexpr int kSmemStack2   = 32;
 constexpr int kDeepStack    = 192;  // entries per thread of the deep kernel's global-memory stack
 
 struct Vec3 { float x, y, z; };
@@ -164,13 +168,14 @@ __device__ __forceinline__ void transform_ray(const InstanceRecord* rec, Vec3 o,
 
 // Traversal stack of the main kernel: kSmemStack entries per thread in shared memory, laid out [level][thread]
 // (bank = lane, conflict free).  push() refuses the entry that does not fit; the ray is then handed to the deep kernel.
+template <int kEntries>
 struct SmemStack
 {
     uint32_t* base;  // &s_stack[tid]
     int       sp;
     __device__ __forceinline__ bool push(uint32_t v)
     {
-        if (sp >= kSmemStack) return false;
+        if (sp >= kEntries) return false;
         base[sp * kTraceThreads] = v;
         ++sp;
         return true;
@@ -349,11 +354,12 @@ overflow:
 template <bool kAny, bool kFullHit, bool kTwoLevel>
 __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(TraceParams P)
 {
-    __shared__ uint32_t s_stack[kSmemStack * kTraceThreads];
+    constexpr int kEntries = kTwoLevel ? kSmemStack2 : kSmemStack1;
+    __shared__ uint32_t s_stack[kEntries * kTraceThreads];
     uint32_t count = P.ray_count;
     if (P.indirect) count = min(count, __ldg(P.indirect));  // isect.comp:98-103
     const uint32_t lane = threadIdx.x & 31;
-    SmemStack st;
+    SmemStack<kEntries> st;
     st.base = s_stack + threadIdx.x;
     while (true)
     {
