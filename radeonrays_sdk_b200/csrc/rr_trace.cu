@@ -327,11 +327,11 @@ __device__ __forceinline__ void trace_ray(const TraceParams& P, StackT& st, uint
             }
             const float4* np = reinterpret_cast<const float4*>(hb + closest_addr);
             const float2  uv = barycentrics(ray, closest, __ldg(np), __ldg(np + 1), __ldg(np + 2));
-            reinterpret_cast<float4*>(P.hits)[gidx] =
-                make_float4(uv.x, uv.y, __uint_as_float(kTwoLevel ? closest_inst : 0u), __uint_as_float(closest_prim));
+            __stcs(reinterpret_cast<float4*>(P.hits) + gidx,
+                   make_float4(uv.x, uv.y, __uint_as_float(kTwoLevel ? closest_inst : 0u), __uint_as_float(closest_prim)));
         }
         else
-            reinterpret_cast<uint32_t*>(P.hits)[gidx] = kTwoLevel ? closest_inst : closest_prim;
+            __stcs(reinterpret_cast<uint32_t*>(P.hits) + gidx, kTwoLevel ? closest_inst : closest_prim);
     }
     else
     {   // miss: only the id word is written (isect.comp:238-245)
@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(Tra
         const uint32_t gidx  = chunk * 32 + lane;
         const bool     valid = gidx < count;
         const uint32_t ridx  = valid ? gidx : count - 1;  // tail lanes shadow the last ray and write nothing
-        const float4 r0 = __ldg(P.rays + 2 * (size_t)ridx), r1 = __ldg(P.rays + 2 * (size_t)ridx + 1);
+        // rays are read once: streaming loads (evict-first) keep them from displacing BVH nodes in L1 / L2
+        const float4 r0 = __ldcs(P.rays + 2 * (size_t)ridx), r1 = __ldcs(P.rays + 2 * (size_t)ridx + 1);
         RayState ray;
         ray.set(v3(r0), v3(r1));
         int oct = 8;
