@@ -884,6 +884,8 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+constexpr int kRefitSlots = 16;  // words per 32-leaf group handed from k_refit_leaves to k_refit_window: count + up to 15 node ids
+
 // Stage 1 of the staged refit, warp-cooperative: one persistent warp per 32 consecutive leaves (node order = sorted leaf
 // order), gather software-pipelined like k_emit_leaves.  Subtrees of an LBVH cover contiguous leaf runs, so the sibling of
 // a finished subtree is the neighbouring finished subtree of the warp whenever their parent lies inside the 32 leaves:
@@ -894,8 +896,8 @@ __global__ void __launch_bounds__(256)
 // announced itself.  (Re-deriving the hierarchy in closed form from deltas kept in the leaves, as the build does, was
 // measured too: 3.8 ms against 3.1 ms at 50 M triangles -- the extra scattered word loads cost more than the rounds.)
 __global__ void __launch_bounds__(256, 3)
-    k_refit_leaves(MeshDesc m, Node* __restrict__ nodes, uint32_t n, uint32_t* __restrict__ out_count, uint32_t* __restrict__ out_items,
-                   uint32_t capacity)
+    k_refit_leaves(MeshDesc m, Node* __restrict__ nodes, uint32_t n, uint32_t* __restrict__ slots, uint32_t* __restrict__ out_count,
+                   uint32_t* __restrict__ out_items, uint32_t capacity)
 {
     const uint32_t full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -1025,12 +1027,122 @@ __global__ void __launch_bounds__(256, 3)
                 own &= ~__reduce_or_sync(full, can ? (1u << nxt) : 0u);
                 owner = (own >> lane) & 1u;
             }
-            hand_over(owner && par != kInvalid, cur, false, 0u);  // (the root has no parent and is done)
+            // what is still waiting for a sibling goes, in leaf order, to this group's slots for k_refit_window (the root has no
+            // parent and is done); more than kRefitSlots - 1 of them (never seen) overflow into the stage-3 list
+            const bool     over = owner && par != kInvalid;
+            const uint32_t om   = __ballot_sync(full, over);
+            const int      rank = __popc(om & ((1u << lane) - 1u));
+            uint32_t*      gs   = slots + (size_t)g * kRefitSlots;
+            if (lane == 0) gs[0] = (uint32_t)min(__popc(om), kRefitSlots - 1);
+            if (over && rank < kRefitSlots - 1) gs[1 + rank] = cur;
+            hand_over(over && rank >= kRefitSlots - 1, cur, false, 0u);
         }
         tri_c = tri_1; w_c = w_1;
         idx_1 = idx_2; w_1 = w_2;
         w_2 = w_3;
     }
+}
+
+// Stage 2 of the staged refit for large meshes: one warp per 512-leaf window over what its 16 groups handed over (~100 finished
+// subtrees, in leaf order).  Same sibling pairing by shuffles as k_refit_leaves, 32 subtrees at a time with their boxes read
+// back from the node images, in passes (the grouping shifted by half a group every other pass) until nothing pairs any more;
+// the rest (~2 % of the leaves: sibling outside the window) goes to the parity-rendezvous climb of k_refit<false>.
+__global__ void __launch_bounds__(256)
+    k_refit_window(Node* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ slots, uint32_t* __restrict__ out_count,
+                   uint32_t* __restrict__ out_items, uint32_t capacity)
+{
+    __shared__ uint32_t s_list[8][2][16 * (kRefitSlots - 1) + 16];
+    const uint32_t full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int leaf0 = (int)n - 1, ngroups = ((int)n + 31) >> 5;
+    const int w = blockIdx.x * 8 + wi, gbase = w * 16;
+    if (gbase >= ngroups) return;
+    const int ngrp = min(16, ngroups - gbase);
+    // concatenate the slots of the groups
+    int M;
+    {
+        const uint32_t c = lane < ngrp ? slots[(size_t)(gbase + lane) * kRefitSlots] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(full, incl, d);
+            if (lane >= d) incl += t;
+        }
+        M = (int)__shfl_sync(full, incl, 15);
+        const uint32_t* gs = slots + (size_t)(gbase + lane) * kRefitSlots + 1;
+        for (uint32_t r = 0; r < c; ++r) s_list[wi][0][incl - c + r] = gs[r];
+    }
+    __syncwarp();
+    int  cur = 0;
+    bool prev_formed = true;
+    for (int pass = 1; M > 1 && pass < 64; ++pass)
+    {
+        const int off = (M > 32 && (pass & 1)) ? 16 : 0;
+        const int ngr = off ? 1 + (M - 16 + 31) / 32 : (M + 31) / 32;
+        int  Mn = 0;
+        bool any = false;
+        for (int q = 0; q < ngr; ++q)
+        {
+            const int e0 = off ? (q == 0 ? 0 : 16 + (q - 1) * 32) : q * 32;
+            const int e1 = min(M, off && q == 0 ? 16 : e0 + 32);
+            const int e  = e0 + lane;
+            bool      owner = e < e1;
+            uint32_t  id = 0, par = kInvalid;
+            float3    lo = make_float3(0.f, 0.f, 0.f), hi = lo;
+            if (owner)
+            {
+                id = s_list[wi][cur][e];
+                const float4* np = reinterpret_cast<const float4*>(nodes + id);
+                const float4  q0 = __ldcg(np), q1 = __ldcg(np + 1), q2 = __ldcg(np + 2), q3 = __ldcg(np + 3);
+                node_box(q0, q1, q2, q3, id >= (uint32_t)leaf0, lo, hi);
+                par = wbits(q2);
+            }
+            uint32_t own = __ballot_sync(full, owner);
+            while (true)
+            {
+                const uint32_t above = own & ~((2u << lane) - 1u);
+                const int      nxt   = above ? __ffs(above) - 1 : lane;
+                const uint32_t npar  = __shfl_sync(full, par, nxt);
+                const bool     can   = owner && above != 0 && npar == par && par != kInvalid;
+                if (__ballot_sync(full, can) == 0) break;
+                any = true;
+                const int src = can ? nxt : lane;
+                float3 nlo, nhi;
+                nlo.x = __shfl_sync(full, lo.x, src); nlo.y = __shfl_sync(full, lo.y, src); nlo.z = __shfl_sync(full, lo.z, src);
+                nhi.x = __shfl_sync(full, hi.x, src); nhi.y = __shfl_sync(full, hi.y, src); nhi.z = __shfl_sync(full, hi.z, src);
+                if (can)
+                {
+                    const uint32_t* pw = reinterpret_cast<const uint32_t*>(nodes + par);
+                    const uint32_t  c0 = __ldcg(pw + 3), c1 = __ldcg(pw + 7), up = __ldcg(pw + 11), upd = __ldcg(pw + 15);
+                    const bool      first = c0 == id;  // which of the two is child0
+                    st_node(nodes + par, pack(first ? lo : nlo, c0), pack(first ? hi : nhi, c1), pack(first ? nlo : lo, up),
+                            pack(first ? nhi : hi, upd));
+                    lo = min3(lo, nlo);
+                    hi = max3(hi, nhi);
+                    id = par;
+                    par = up;
+                }
+                own &= ~__reduce_or_sync(full, can ? (1u << nxt) : 0u);
+                owner = (own >> lane) & 1u;
+            }
+            const bool     over = owner && par != kInvalid;
+            const uint32_t om   = __ballot_sync(full, over);
+            if (over) s_list[wi][cur ^ 1][Mn + __popc(om & ((1u << lane) - 1u))] = id;
+            Mn += __popc(om);
+            __syncwarp();
+        }
+        M = Mn;
+        cur ^= 1;
+        if (ngr == 1 || (!any && !prev_formed)) break;
+        prev_formed = any;
+    }
+    // the rest continues with the parity rendezvous (stage 3)
+    uint32_t base = 0;
+    if (lane == 0 && M > 0) base = atomicAdd(out_count, (uint32_t)M);
+    base = __shfl_sync(full, base, 0);
+    for (int e = lane; e < M; e += 32)
+        if (base + e < capacity) out_items[base + e] = s_list[wi][cur][e];
 }
 
 // ---- K8: instance world boxes + scene AABB (lbvh_calc_scene_aabb.comp:131-163, common.h:270-308) -------
@@ -1193,9 +1305,12 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
 
 // Update scratch: [256 B: the two list counters | list A 4 x capacity | list B 4 x capacity], capacity = n/4 + 256:
 // a hand-over after k levels implies a finished subtree of >= k+1 leaves, so stage 1 (3 levels) emits <= n/4 entries.
+constexpr uint32_t kRefitWarpPathMin = 500000u;  // triangles from which stage 1 / 2 are the warp-cooperative kernels
 size_t update_scratch_size(uint32_t n)
 {
     const size_t cap = (size_t)n / 4 + 256;
+    if (n >= kRefitWarpPathMin)  // counters | stage-3 list | 16 words per 32-leaf group between k_refit_leaves and k_refit_window
+        return 256 + align_up(sizeof(uint32_t) * cap, 256) + align_up(sizeof(uint32_t) * kRefitSlots * (((size_t)n + 31) / 32), 256);
     return 256 + 2 * align_up(sizeof(uint32_t) * cap, 256);
 }
 
@@ -1220,16 +1335,25 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
     L.items_b = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (size_t)cap, 256));
     L.capacity = cap;
     RR_CUDA_CHECK(cudaMemsetAsync(sc, 0, 8, s));
-    // stage 1: warp-cooperative persistent kernel for large meshes; for small ones its pipeline prologue costs more than it
-    // hides (Sponza, 262 k triangles: 0.150 against 0.133 ms) and the one-thread-per-leaf version (3 levels) is used
-    if (n >= 500000u)
-        k_refit_leaves<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)dev.sm_count * 3u), 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, cap);
+    if (n >= kRefitWarpPathMin)
+    {   // large meshes: warp-cooperative stages 1 (per 32 leaves) and 2 (per 512-leaf window), then the parity-rendezvous climb
+        // for the ~2 % that is left.  For small ones the pipeline prologue of the persistent kernel costs more than it hides
+        // (Sponza, 262 k triangles: 0.150 against 0.133 ms).
+        uint32_t* slots = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (size_t)cap, 256));
+        k_refit_leaves<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)dev.sm_count * 3u), 256, 0, s>>>(mesh, nodes, n, slots, L.count_a, L.items_a, cap);
+        const uint32_t windows = (n + kEmitWindow - 1) / kEmitWindow;
+        k_refit_window<<<(windows + 7) / 8, 256, 0, s>>>(nodes, n, slots, L.count_a, L.items_a, cap);
+        const uint32_t grid3 = std::min<uint32_t>((cap + 255) / 256, (uint32_t)dev.sm_count * 32u);
+        k_refit<false><<<grid3, 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, kUnbounded, nullptr, nullptr, cap);
+    }
     else
+    {
         k_refit<true><<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n, nullptr, nullptr, 3u, L.count_a, L.items_a, cap);
-    const uint32_t grid2 = std::min<uint32_t>((cap + 255) / 256, (uint32_t)dev.sm_count * 64u);
-    k_refit<false><<<grid2, 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, 6u, L.count_b, L.items_b, cap);
-    const uint32_t grid3 = std::min<uint32_t>((cap / 64 + 255) / 256 + 1, (uint32_t)dev.sm_count * 16u);
-    k_refit<false><<<grid3, 256, 0, s>>>(mesh, nodes, n, L.count_b, L.items_b, kUnbounded, nullptr, nullptr, cap);
+        const uint32_t grid2 = std::min<uint32_t>((cap + 255) / 256, (uint32_t)dev.sm_count * 64u);
+        k_refit<false><<<grid2, 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, 6u, L.count_b, L.items_b, cap);
+        const uint32_t grid3 = std::min<uint32_t>((cap / 64 + 255) / 256 + 1, (uint32_t)dev.sm_count * 16u);
+        k_refit<false><<<grid3, 256, 0, s>>>(mesh, nodes, n, L.count_b, L.items_b, kUnbounded, nullptr, nullptr, cap);
+    }
     *dev.launches += 3;
     RR_CUDA_CHECK(cudaGetLastError());
 }
