@@ -895,7 +895,7 @@ constexpr int kRefitSlots = 16;  // words per 32-leaf group handed from k_refit_
 // continues with the parity rendezvous of k_refit.  The update word of a node fitted here keeps its parity: neither child
 // announced itself.  (Re-deriving the hierarchy in closed form from deltas kept in the leaves, as the build does, was
 // measured too: 3.8 ms against 3.1 ms at 50 M triangles -- the extra scattered word loads cost more than the rounds.)
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)  // 64 registers; 3 / 5 / 6 CTAs per SM: 3.84 / 3.88 / 4.58 ms refit at 50 M triangles against 3.60
     k_refit_leaves(MeshDesc m, Node* __restrict__ nodes, uint32_t n, uint32_t* __restrict__ slots, uint32_t* __restrict__ out_count,
                    uint32_t* __restrict__ out_items, uint32_t capacity)
 {
@@ -1340,7 +1340,7 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
         // for the ~2 % that is left.  For small ones the pipeline prologue of the persistent kernel costs more than it hides
         // (Sponza, 262 k triangles: 0.150 against 0.133 ms).
         uint32_t* slots = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (size_t)cap, 256));
-        k_refit_leaves<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)dev.sm_count * 3u), 256, 0, s>>>(mesh, nodes, n, slots, L.count_a, L.items_a, cap);
+        k_refit_leaves<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)dev.sm_count * 4u), 256, 0, s>>>(mesh, nodes, n, slots, L.count_a, L.items_a, cap);
         const uint32_t windows = (n + kEmitWindow - 1) / kEmitWindow;
         k_refit_window<<<(windows + 7) / 8, 256, 0, s>>>(nodes, n, slots, L.count_a, L.items_a, cap);
         const uint32_t grid3 = std::min<uint32_t>((cap + 255) / 256, (uint32_t)dev.sm_count * 32u);
