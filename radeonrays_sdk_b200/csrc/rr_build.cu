@@ -125,12 +125,18 @@ __global__ void __launch_bounds__(256) k_scene_aabb(MeshDesc m, uint32_t* __rest
     OrderedBox box;
     box.init();
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m.triangle_count; i += stride)
+    // two triangles per iteration: twice the loads in flight per thread (the sweep is latency-, not bandwidth-bound)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m.triangle_count; i += 2 * stride)
     {
+        const uint32_t k  = min(i + stride, m.triangle_count - 1);  // second triangle (clamped: min/max are idempotent)
         const uint32_t i0 = m.indices[3 * (size_t)i + 0], i1 = m.indices[3 * (size_t)i + 1], i2 = m.indices[3 * (size_t)i + 2];
-        box.grow(ld3(m.vertices + (size_t)i0 * m.stride_floats));
-        box.grow(ld3(m.vertices + (size_t)i1 * m.stride_floats));
-        box.grow(ld3(m.vertices + (size_t)i2 * m.stride_floats));
+        const uint32_t k0 = m.indices[3 * (size_t)k + 0], k1 = m.indices[3 * (size_t)k + 1], k2 = m.indices[3 * (size_t)k + 2];
+        const float3   a0 = ld3(m.vertices + (size_t)i0 * m.stride_floats), a1 = ld3(m.vertices + (size_t)i1 * m.stride_floats),
+                       a2 = ld3(m.vertices + (size_t)i2 * m.stride_floats);
+        const float3   b0 = ld3(m.vertices + (size_t)k0 * m.stride_floats), b1 = ld3(m.vertices + (size_t)k1 * m.stride_floats),
+                       b2 = ld3(m.vertices + (size_t)k2 * m.stride_floats);
+        box.grow(a0); box.grow(a1); box.grow(a2);
+        box.grow(b0); box.grow(b1); box.grow(b2);
     }
     reduce_box_to_global(box, g_aabb);
 }
@@ -155,6 +161,7 @@ __global__ void __launch_bounds__(256)
     float3 smin, smax;
     load_scene_box(g_aabb, smin, smax);
     const uint32_t stride = gridDim.x * blockDim.x;
+    // (two primitives per iteration, as in k_scene_aabb, measured slower here: 371 against 282 us at 50 M triangles)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
     {
         float3 bmin, bmax;
