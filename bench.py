@@ -278,7 +278,7 @@ def run_ours(args):
                      "l1_data_pipe": {"lane_visits_per_ray": LANE_VISITS_PER_RAY, "peak_visits_per_s": round(l1_peak_visits, 1),
                                       "achieved_visits_per_s": round(LANE_VISITS_PER_RAY * n_rays / (ms_step * 1e-3), 1),
                                       "frac": round(LANE_VISITS_PER_RAY * n_rays / (ms_step * 1e-3) / l1_peak_visits, 4),
-                                      "ncu_l1tex_data_pipe_pct": 87.0, "source": "profiles/round1_summary.md section 2"}},
+                                      "ncu_l1tex_data_pipe_pct": 91.2, "source": "profiles/round1_summary.md section 2"}},
         "cpu_baseline": cpu,
         "clocks": clocks,
         "build": {"fast_ms": round(ms_fast, 4), "fast_mtris_per_s": round(n_tris / ms_fast / 1e3, 1), "quality_ms": round(ms_qual, 4),
