@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <cuda.h>  // CUtensorMap (encoded through the runtime's driver entry point: libcuda is not linked)
+
 #include "rr_internal.h"
 
 namespace rr
@@ -205,6 +207,7 @@ struct EmitParams
     uint32_t        n;
     Node*           nodes;
     uint32_t*       lists;   // per 512-leaf window: count + up to kListSlots left ends of the subtrees k_emit_window left over
+    bool            tma;     // k_emit_leaves stages node images in shared memory and stores them with TMA tensor copies
     uint32_t*       masks;             // [ceil(n/32)] per 32 leaves: left ends of the subtrees k_emit_leaves left over
     // mesh leaves
     MeshDesc mesh;
@@ -292,6 +295,8 @@ __device__ __forceinline__ void st_node(Node* dst, float4 q0, float4 q1, float4 
                  "f"(q3.x), "f"(q3.y), "f"(q3.z), "f"(q3.w)
                  : "memory");
 }
+
+__device__ __forceinline__ void st_node_direct(Node* dst, float4 q0, float4 q1, float4 q2, float4 q3) { st_node(dst, q0, q1, q2, q3); }
 
 // Range min (kMin) / max over lanes [Ll, lane] -> outL and [lane+1, pr] -> outR of a per-lane value: four doubling
 // steps build the windows "2^k lanes ending here", the two ranges are then covered by the binary digits of their lengths.
@@ -413,7 +418,8 @@ constexpr int kLeavesCtasPerSm = 3;  // 80 registers; 4 / 5 / 6 CTAs per SM meas
 // vertex loads of g+1, the index loads of g+2 and the ref/code loads of g+3 are in flight, so the dependent chain
 // ref -> indices -> vertices (three DRAM latencies) never stalls the warp (it was 72 % of the stall samples).
 template <bool kScene>
-__global__ void __launch_bounds__(256, kLeavesCtasPerSm) k_emit_leaves(EmitParams p)
+__global__ void __launch_bounds__(256, kLeavesCtasPerSm)
+    k_emit_leaves(EmitParams p, const __grid_constant__ CUtensorMap tm_leaf, const __grid_constant__ CUtensorMap tm_node)
 {
     const uint32_t full = 0xffffffffu;
     const int n = (int)p.n, leaf0 = n - 1, lane = threadIdx.x & 31;
@@ -485,6 +491,25 @@ __global__ void __launch_bounds__(256, kLeavesCtasPerSm) k_emit_leaves(EmitParam
         return Tri{ld_vertex(verts, (size_t)i.i0 * vstride, base8), ld_vertex(verts, (size_t)i.i1 * vstride, base8),
                    ld_vertex(verts, (size_t)i.i2 * vstride, base8)};
     };
+    // Node images leave through the TMA when p.tma: a 64-byte-strided STG costs the L1 data pipe one wavefront per 32-byte
+    // sector (106 of this kernel's 276 wavefronts per group).  Each warp stages its 32 leaves and the 32 internal slots of its
+    // group as two dense 2 KB blocks in shared memory -- 16-byte quads XOR-swizzled exactly as CU_TENSOR_MAP_SWIZZLE_64B
+    // expects (chunk ^= (row >> 1) & 3), which makes the per-lane 16-byte stores conflict free -- and one lane issues two
+    // tensor copies.  Internal slots the group did not form are written with stale bytes: they belong to nodes that a later
+    // kernel of the emission forms (and writes whole), never to another group; rows past the arrays are clipped by the maps.
+    __shared__ __align__(1024) unsigned char s_stage[8][2][2048];
+    unsigned char* st_leaf = s_stage[threadIdx.x >> 5][0];
+    unsigned char* st_node = s_stage[threadIdx.x >> 5][1];
+    const bool     tma     = p.tma;
+    auto quad_at = [](unsigned char* base, int row, int k) -> float4* {
+        return reinterpret_cast<float4*>(base + row * 64 + ((k ^ ((row >> 1) & 3)) << 4));
+    };
+    int  wb_now = 0;
+    auto staged_store = [&](uint32_t idx, float4 q0, float4 q1, float4 q2, float4 q3) {
+        if (!tma) { st_node_direct(p.nodes + idx, q0, q1, q2, q3); return; }
+        const int row = (int)idx - wb_now;
+        *quad_at(st_node, row, 0) = q0; *quad_at(st_node, row, 1) = q1; *quad_at(st_node, row, 2) = q2; *quad_at(st_node, row, 3) = q3;
+    };
     // prologue
     uint32_t ref_c = p.refs[leaf_of(g0)];
     Codes    cod_c = load_codes(g0);
@@ -512,13 +537,38 @@ __global__ void __launch_bounds__(256, kLeavesCtasPerSm) k_emit_leaves(EmitParam
         // lbvh_fit_aabb_mesh.comp:139-163
         const float3 lo = min3(min3(tri_c.v0, tri_c.v1), tri_c.v2), hi = max3(max3(tri_c.v0, tri_c.v1), tri_c.v2);
         const float3 v2 = tri_c.v2;
-        if (valid)
+        wb_now = wb;
+        if (tma)
+        {   // the staging blocks are free again once the previous group's copies have read them
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            *quad_at(st_leaf, lane, 0) = pack(tri_c.v0, kInvalid);
+            *quad_at(st_leaf, lane, 1) = pack(tri_c.v1, ref_c);
+        }
+        else if (valid)
             asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p.nodes + leaf0 + j), "f"(tri_c.v0.x),
                          "f"(tri_c.v0.y), "f"(tri_c.v0.z), "f"(__uint_as_float(kInvalid)), "f"(tri_c.v1.x), "f"(tri_c.v1.y), "f"(tri_c.v1.z),
                          "f"(__uint_as_float(ref_c))
                          : "memory");
-        const MergeOut o = group_merge<true>(direct_store, n, cnt, valid, j, j, (uint32_t)(leaf0 + j), lo, hi, D, DL0);
-        if (valid)
+        const MergeOut o = group_merge<true>(staged_store, n, cnt, valid, j, j, (uint32_t)(leaf0 + j), lo, hi, D, DL0);
+        if (tma)
+        {
+            *quad_at(st_leaf, lane, 2) = pack(v2, o.e_parent);
+            *quad_at(st_leaf, lane, 3) = make_float4(0.f, 0.f, 0.f, 0.f);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0)
+            {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tm_leaf)),
+                             "r"((uint32_t)__cvta_generic_to_shared(st_leaf)), "r"(0), "r"(wb)
+                             : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tm_node)),
+                             "r"((uint32_t)__cvta_generic_to_shared(st_node)), "r"(0), "r"(wb)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        else if (valid)
             asm volatile("st.global.v8.f32 [%0+32], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p.nodes + leaf0 + j), "f"(v2.x), "f"(v2.y),
                          "f"(v2.z), "f"(__uint_as_float(o.e_parent)), "f"(0.f), "f"(0.f), "f"(0.f), "f"(0.f)
                          : "memory");
@@ -529,6 +579,7 @@ __global__ void __launch_bounds__(256, kLeavesCtasPerSm) k_emit_leaves(EmitParam
         idx_1 = idx_2; ref_1 = ref_2; cod_1 = cod_2;
         ref_2 = ref_3;
     }
+    if (tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the copies are complete before the warp retires
 }
 
 // Box of a finished node from its image in memory (L2).
@@ -1199,16 +1250,41 @@ __global__ void __launch_bounds__(256)
     reduce_box_to_global(sb, g_aabb);
 }
 
+// Tensor map over `rows` consecutive 64-byte nodes (16 floats per row, 32 rows per box, 64-byte swizzle): the destination of the
+// TMA stores of k_emit_leaves.  cuTensorMapEncodeTiled comes from the runtime's driver entry point; false if unavailable.
+static bool node_tensor_map(CUtensorMap* tm, Node* base, uint64_t rows)
+{
+    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<EncodeFn>(f);
+    }();
+    if (!fn || rows == 0 || rows > 0xFFFFFFFFull || (reinterpret_cast<uintptr_t>(base) & 15u)) return false;
+    const cuuint64_t dims[2]    = {16, rows};
+    const cuuint64_t strides[1] = {sizeof(Node)};
+    const cuuint32_t box[2]     = {16, 32};
+    const cuuint32_t estr[2]    = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Words of the list area one level with `windows` windows needs.
 inline size_t emit_list_words(uint32_t windows) { return align_up((size_t)windows * kListStride, 64); }
 
 template <bool kScene>
-int launch_emit_fit(const DeviceInfo& dev, cudaStream_t s, const EmitParams& p)
+int launch_emit_fit(const DeviceInfo& dev, cudaStream_t s, const EmitParams& p_in)
 {
-    const uint32_t groups = (p.n + 31) / 32, windows = (p.n + kEmitWindow - 1) / kEmitWindow;
+    const uint32_t groups = (p_in.n + 31) / 32, windows = (p_in.n + kEmitWindow - 1) / kEmitWindow;
     // persistent warps: exactly the resident CTAs, so that every warp streams through a long run of groups
     const uint32_t ctas = std::min<uint32_t>((groups + 7) / 8, (uint32_t)(dev.sm_count * kLeavesCtasPerSm));
-    k_emit_leaves<kScene><<<ctas, 256, 0, s>>>(p);
+    EmitParams  p = p_in;
+    CUtensorMap tm_leaf{}, tm_node{};
+    static const bool tma_allowed = [] { const char* e = std::getenv("RR_CUDA_EMIT_TMA"); return !e || std::atoi(e) != 0; }();
+    p.tma = !kScene && tma_allowed && p.n >= 2 && node_tensor_map(&tm_leaf, p.nodes + (p.n - 1), p.n) && node_tensor_map(&tm_node, p.nodes, p.n - 1);
+    k_emit_leaves<kScene><<<ctas, 256, 0, s>>>(p, tm_leaf, tm_node);
     if (p.n <= 32) return 1;  // the whole tree was inside one group
     k_emit_window<kScene><<<(windows + kWindowWarps - 1) / kWindowWarps, 32 * kWindowWarps, 0, s>>>(p);
     int launches = 2;
