@@ -955,8 +955,14 @@ constexpr int kRefitSlots = 16;  // words per 32-leaf group handed from k_refit_
 // measured too: 3.8 ms against 3.1 ms at 50 M triangles -- the extra scattered word loads cost more than the rounds.)
 __global__ void __launch_bounds__(256, 4)  // 64 registers; 3 / 5 / 6 CTAs per SM: 3.84 / 3.88 / 4.58 ms refit at 50 M triangles against 3.60
     k_refit_leaves(MeshDesc m, Node* __restrict__ nodes, uint32_t n, uint32_t* __restrict__ slots, uint32_t* __restrict__ out_count,
-                   uint32_t* __restrict__ out_items, uint32_t capacity)
+                   uint32_t* __restrict__ out_items, uint32_t capacity, const __grid_constant__ CUtensorMap tm_leaf, int tma)
 {
+    // leaves leave through the TMA like in k_emit_leaves (one swizzled 2 KB block per group) when `tma`
+    __shared__ __align__(1024) unsigned char s_stage[8][2048];
+    unsigned char* st_leaf = s_stage[threadIdx.x >> 5];
+    auto quad_at = [](unsigned char* base, int row, int k) -> float4* {
+        return reinterpret_cast<float4*>(base + row * 64 + ((k ^ ((row >> 1) & 3)) << 4));
+    };
     const uint32_t full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int leaf0 = (int)n - 1, ngroups = ((int)n + 31) >> 5, nwarps = gridDim.x * (blockDim.x >> 5);
@@ -1046,7 +1052,25 @@ __global__ void __launch_bounds__(256, 4)  // 64 registers; 3 / 5 / 6 CTAs per S
         const int  j = (g << 5) + lane;
         const bool valid = j < (int)n;
         float3     lo = min3(min3(tri_c.v0, tri_c.v1), tri_c.v2), hi = max3(max3(tri_c.v0, tri_c.v1), tri_c.v2);
-        if (valid)
+        if (tma)
+        {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            *quad_at(st_leaf, lane, 0) = pack(tri_c.v0, kInvalid);
+            *quad_at(st_leaf, lane, 1) = pack(tri_c.v1, w_c.prim);
+            *quad_at(st_leaf, lane, 2) = pack(tri_c.v2, w_c.parent);
+            *quad_at(st_leaf, lane, 3) = make_float4(0.f, 0.f, 0.f, 0.f);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0)
+            {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tm_leaf)),
+                             "r"((uint32_t)__cvta_generic_to_shared(st_leaf)), "r"(0), "r"(g << 5)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        else if (valid)
             st_node(nodes + leaf0 + j, pack(tri_c.v0, kInvalid), pack(tri_c.v1, w_c.prim), pack(tri_c.v2, w_c.parent),
                     make_float4(0.f, 0.f, 0.f, 0.f));
         {
@@ -1099,6 +1123,7 @@ __global__ void __launch_bounds__(256, 4)  // 64 registers; 3 / 5 / 6 CTAs per S
         idx_1 = idx_2; w_1 = w_2;
         w_2 = w_3;
     }
+    if (tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Stage 2 of the staged refit for large meshes: one warp per 512-leaf window over what its 16 groups handed over (~100 finished
@@ -1423,7 +1448,10 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
         // for the ~2 % that is left.  For small ones the pipeline prologue of the persistent kernel costs more than it hides
         // (Sponza, 262 k triangles: 0.150 against 0.133 ms).
         uint32_t* slots = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (size_t)cap, 256));
-        k_refit_leaves<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)dev.sm_count * 4u), 256, 0, s>>>(mesh, nodes, n, slots, L.count_a, L.items_a, cap);
+        CUtensorMap tm_leaf{};
+        const int   tma = node_tensor_map(&tm_leaf, nodes + (n - 1), n) ? 1 : 0;
+        k_refit_leaves<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)dev.sm_count * 4u), 256, 0, s>>>(mesh, nodes, n, slots, L.count_a, L.items_a,
+                                                                                                   cap, tm_leaf, tma);
         const uint32_t windows = (n + kEmitWindow - 1) / kEmitWindow;
         k_refit_window<<<(windows + 7) / 8, 256, 0, s>>>(nodes, n, slots, L.count_a, L.items_a, cap);
         const uint32_t grid3 = std::min<uint32_t>((cap + 255) / 256, (uint32_t)dev.sm_count * 32u);
