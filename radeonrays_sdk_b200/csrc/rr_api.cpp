@@ -155,13 +155,14 @@ static RRError mesh_from_input(const RRGeometryBuildInput* in, MeshDesc& m)
     if (in->primitive_count == 0 || !in->triangle_mesh_primitives) return RR_ERROR_INVALID_PARAMETER;
     if (in->primitive_count != 1) return RR_ERROR_NOT_IMPLEMENTED;
     const RRTriangleMeshPrimitive& p = in->triangle_mesh_primitives[0];
-    if (p.index_type != RR_INDEX_TYPE_UINT32) return RR_ERROR_NOT_IMPLEMENTED;
+    if (p.index_type != RR_INDEX_TYPE_UINT32 && p.index_type != RR_INDEX_TYPE_UINT16) return RR_ERROR_INVALID_PARAMETER;
     if (p.triangle_count == 0 || (p.vertex_stride & 3u) || p.vertex_stride < 12) return RR_ERROR_INVALID_PARAMETER;
     m.vertices       = p.vertices ? reinterpret_cast<const float*>(D(p.vertices)->ptr()) : nullptr;
     m.vertex_count   = p.vertex_count;
     m.stride_floats  = p.vertex_stride >> 2;
     m.indices        = p.triangle_indices ? reinterpret_cast<const uint32_t*>(D(p.triangle_indices)->ptr()) : nullptr;
     m.triangle_count = p.triangle_count;
+    m.index16        = p.index_type == RR_INDEX_TYPE_UINT16 ? 1u : 0u;  // beyond the reference, which reads 32-bit indices whatever index_type says
     return RR_SUCCESS;
 }
 }  // namespace rr

@@ -31,6 +31,20 @@ __device__ __forceinline__ uint32_t float_to_ordered(float f)
 __device__ __forceinline__ float ordered_to_float(uint32_t v) { return __uint_as_float(v ^ (((v >> 31) - 1u) | 0x80000000u)); }
 
 __device__ __forceinline__ float3 ld3(const float* p) { return make_float3(p[0], p[1], p[2]); }
+// The three vertex indices of a triangle: 32-bit, or 16-bit when the mesh says so (RR_INDEX_TYPE_UINT16).
+__device__ __forceinline__ void tri_indices(const MeshDesc& m, size_t prim, uint32_t& i0, uint32_t& i1, uint32_t& i2)
+{
+    if (m.index16)
+    {
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(m.indices) + 3 * prim;
+        i0 = p[0]; i1 = p[1]; i2 = p[2];
+    }
+    else
+    {
+        const uint32_t* p = m.indices + 3 * prim;
+        i0 = p[0]; i1 = p[1]; i2 = p[2];
+    }
+}
 // A vertex as one 8-byte and one 4-byte load: its 12 bytes start at a multiple of 4, so either half may be the aligned
 // one (base8: the vertex buffer itself is 8-byte aligned).  Two L1 requests instead of three; pays where lanes gather
 // scattered vertices (k_emit_leaves), not in the sweeps over triangles in input order (measured 30 % slower there).
@@ -131,8 +145,9 @@ __global__ void __launch_bounds__(256) k_scene_aabb(MeshDesc m, uint32_t* __rest
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m.triangle_count; i += 2 * stride)
     {
         const uint32_t k  = min(i + stride, m.triangle_count - 1);  // second triangle (clamped: min/max are idempotent)
-        const uint32_t i0 = m.indices[3 * (size_t)i + 0], i1 = m.indices[3 * (size_t)i + 1], i2 = m.indices[3 * (size_t)i + 2];
-        const uint32_t k0 = m.indices[3 * (size_t)k + 0], k1 = m.indices[3 * (size_t)k + 1], k2 = m.indices[3 * (size_t)k + 2];
+        uint32_t i0, i1, i2, k0, k1, k2;
+        tri_indices(m, i, i0, i1, i2);
+        tri_indices(m, k, k0, k1, k2);
         const float3   a0 = ld3(m.vertices + (size_t)i0 * m.stride_floats), a1 = ld3(m.vertices + (size_t)i1 * m.stride_floats),
                        a2 = ld3(m.vertices + (size_t)i2 * m.stride_floats);
         const float3   b0 = ld3(m.vertices + (size_t)k0 * m.stride_floats), b1 = ld3(m.vertices + (size_t)k1 * m.stride_floats),
@@ -174,7 +189,8 @@ __global__ void __launch_bounds__(256)
         }
         else
         {
-            const uint32_t i0 = m.indices[3 * (size_t)i + 0], i1 = m.indices[3 * (size_t)i + 1], i2 = m.indices[3 * (size_t)i + 2];
+            uint32_t i0, i1, i2;
+            tri_indices(m, i, i0, i1, i2);
             const float3   v0 = ld3(m.vertices + (size_t)i0 * m.stride_floats);
             const float3   v1 = ld3(m.vertices + (size_t)i1 * m.stride_floats);
             const float3   v2 = ld3(m.vertices + (size_t)i2 * m.stride_floats);
@@ -466,7 +482,6 @@ __global__ void __launch_bounds__(256, kLeavesCtasPerSm)
     }
     if (g0 >= ngroups) return;
     const float*    verts   = p.mesh.vertices;
-    const uint32_t* indices = p.mesh.indices;
     const size_t    vstride = p.mesh.stride_floats;
     // loads of a group that may lie past the end are clamped to the last leaf (results unused)
     auto leaf_of = [&](int g) -> int { return min((g << 5) + lane, n - 1); };
@@ -482,8 +497,9 @@ __global__ void __launch_bounds__(256, kLeavesCtasPerSm)
     };
     struct Idx { uint32_t i0, i1, i2; };
     auto load_idx = [&](uint32_t ref) -> Idx {
-        const uint32_t* ip = indices + 3 * (size_t)ref;
-        return Idx{ip[0], ip[1], ip[2]};
+        Idx i;
+        tri_indices(p.mesh, ref, i.i0, i.i1, i.i2);
+        return i;
     };
     struct Tri { float3 v0, v1, v2; };
     const bool base8 = (reinterpret_cast<uintptr_t>(verts) & 7u) == 0;
@@ -872,7 +888,8 @@ __global__ void __launch_bounds__(256)
                 const float4 q1 = np[1], q2 = np[2];
                 const uint32_t prim = wbits(q1);
                 parent = wbits(q2);
-                const uint32_t i0 = m.indices[3 * (size_t)prim + 0], i1 = m.indices[3 * (size_t)prim + 1], i2 = m.indices[3 * (size_t)prim + 2];
+                uint32_t i0, i1, i2;
+                tri_indices(m, prim, i0, i1, i2);
                 const float3 v0 = ld3(m.vertices + (size_t)i0 * m.stride_floats);
                 const float3 v1 = ld3(m.vertices + (size_t)i1 * m.stride_floats);
                 const float3 v2 = ld3(m.vertices + (size_t)i2 * m.stride_floats);
@@ -969,7 +986,6 @@ __global__ void __launch_bounds__(256, 4)  // 64 registers; 3 / 5 / 6 CTAs per S
     const int g0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g0 >= ngroups) return;
     const float*    verts   = m.vertices;
-    const uint32_t* indices = m.indices;
     const size_t    vstride = m.stride_floats;
     const bool      base8   = (reinterpret_cast<uintptr_t>(verts) & 7u) == 0;
     auto leaf_of = [&](int g) -> int { return min((g << 5) + lane, (int)n - 1); };
@@ -980,8 +996,9 @@ __global__ void __launch_bounds__(256, 4)  // 64 registers; 3 / 5 / 6 CTAs per S
     };
     struct Idx { uint32_t i0, i1, i2; };
     auto load_idx = [&](uint32_t prim) -> Idx {
-        const uint32_t* ip = indices + 3 * (size_t)prim;
-        return Idx{ip[0], ip[1], ip[2]};
+        Idx i;
+        tri_indices(m, prim, i.i0, i.i1, i.i2);
+        return i;
     };
     struct Tri { float3 v0, v1, v2; };
     auto load_tri = [&](const Idx& i) -> Tri {

@@ -101,8 +101,9 @@ struct MeshDesc
     const float*    vertices;       // device
     uint32_t        vertex_count;
     uint32_t        stride_floats;  // vertex_stride >> 2 (lbvh_calc_mesh_aabb.comp:128)
-    const uint32_t* indices;        // device, 3 per triangle (index_type ignored like the reference)
+    const uint32_t* indices;        // device, 3 per triangle: u32, or u16 when index16 (RR_INDEX_TYPE_UINT16; the reference ignores index_type)
     uint32_t        triangle_count;
+    uint32_t        index16;        // 1: indices are 16-bit
 };
 struct BlasLayout
 {

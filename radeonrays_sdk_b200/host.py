@@ -47,7 +47,8 @@ class Engine:
         g = Geometry()
         g.engine = self
         positions = np.ascontiguousarray(positions, np.float32)
-        indices = np.ascontiguousarray(indices, np.uint32)
+        index16 = np.asarray(indices).dtype == np.uint16                 # RR_INDEX_TYPE_UINT16 (beyond the reference)
+        indices = np.ascontiguousarray(indices, np.uint16 if index16 else np.uint32)
         g.triangle_count = int(indices.shape[0])
         g.vertex_count = int(positions.shape[0])
         g.vertex_stride = int(vertex_stride or positions.shape[1] * 4)
@@ -57,7 +58,8 @@ class Engine:
         ctx = self.ctx
         g.p_vertices = ctx.tensor_ptr(g.d_vertices)
         g.p_indices = ctx.tensor_ptr(g.d_indices)
-        g.input = ctx.geometry_input(g.p_vertices, g.vertex_count, g.vertex_stride, g.p_indices, g.triangle_count)
+        g.input = ctx.geometry_input(g.p_vertices, g.vertex_count, g.vertex_stride, g.p_indices, g.triangle_count,
+                                     api.RR_INDEX_TYPE_UINT16 if index16 else api.RR_INDEX_TYPE_UINT32)
         g.req = ctx.geometry_requirements(g.input, g.options)
         g.d_temp = _dev_bytes(g.req.temporary_build_buffer_size, self.device)
         g.d_nodes = _dev_bytes(g.req.result_buffer_size, self.device)

@@ -134,6 +134,29 @@ def test_duplicate_and_degenerate_inputs(engine):
     assert_nodes_equal(g.nodes(), want)
 
 
+def test_uint16_indices(engine, cornell):
+    """RR_INDEX_TYPE_UINT16 (beyond the reference, which reads 32-bit indices whatever index_type says):
+    same BVH, refit and hits as the 32-bit mesh."""
+    rng = np.random.default_rng(16)
+    n_v, n = 60000, 70000                                  # > 65535 triangles, all vertex ids fit 16 bits; refit takes the staged path
+    pos = rng.random((n_v, 3), dtype=np.float32)
+    idx = rng.integers(0, n_v, (n, 3)).astype(np.uint32)
+    g16 = engine.build_geometry(pos, idx.astype(np.uint16))
+    want, _, _ = O.build_blas(pos, idx)
+    assert_nodes_equal(g16.nodes(), want, what="uint16 build")
+    moved = (pos * np.float32(0.5)).astype(np.float32)
+    engine.update_geometry(g16, moved)
+    assert_nodes_equal(g16.nodes(), O.refit(want, moved, idx), what="uint16 refit")
+    cpos, cidx, _ = cornell
+    g = engine.build_geometry(cpos, cidx.astype(np.uint16), build_flags=0)
+    rays = W.cornell_primary_rays(64)
+    ref = O.trace(O.build_blas(cpos, cidx, restructure=True)[0], rays)
+    got = engine.intersect(g, rays)
+    assert np.array_equal(got["inst_id"], ref["inst_id"])
+    ok = ref["inst_id"] != O.INVALID
+    assert np.array_equal(got["prim_id"][ok], ref["prim_id"][ok])
+
+
 def test_update_refit(engine, sponza):
     """hlbvh_test.h:445-493 UpdateTest: move every vertex by +10 in y, UPDATE, topology untouched."""
     pos, idx, _ = sponza
