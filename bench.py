@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT = 3840, 2160
 BYTES_PER_RAY = 48           # 32 B ray read + 16 B RRHit write: the compulsory HBM traffic
-TRACE_DRAM_BYTES_PER_LAUNCH = 379_617_792   # dram__bytes_read+write of one C2 launch, ncu --set full (profiles/round1_summary.md)
+TRACE_DRAM_BYTES_PER_LAUNCH = 357_213_952   # dram__bytes_read+write of one C2 launch, ncu --set full (profiles/round1_summary.md)
 LANE_VISITS_PER_RAY = 66.6   # warp-iterations x 32 / rays of the C2 batch on the quality BVH (ncu instruction counts, same file)
 BUILD_BYTES_PER_TRI = 348    # 48 aabb + 48 morton + 4 code + 60 sort + 12 emit reads + 48 gather + 128 nodes
 
@@ -253,6 +253,11 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(geom.nodes(), rays)
 
+    # ---- config C5 on one GPU: HLBVH rebuild vs refit of a 50 M-triangle height field, as a fraction of the HBM roofline -------
+    c5 = None
+    if rank == 0 and world == 1 and not args.no_c5:
+        c5 = build_c5(eng)
+
     peak, peak_src = measured_peak_gbs()
     l1_peak_visits = 2.0 * eng.sm_count * (clocks["sm_max_mhz"] if clocks and clocks.get("sm_max_mhz") else 1965.0) * 1e6
     achieved = BYTES_PER_RAY * n_rays / (ms_step * 1e-3) / 1e9
@@ -285,6 +290,7 @@ def run_ours(args):
                   "quality_mtris_per_s": round(n_tris / ms_qual / 1e3, 1), "refit_ms": round(ms_refit, 4),
                   "refit_mtris_per_s": round(n_tris / ms_refit / 1e3, 1), "launches_per_fast_build": int(launches_per_fast_build),
                   "fast_build_hbm_gbs": round(build_gbs, 1), "fast_build_roofline_frac": round(build_gbs / peak, 4)},
+        "build_c5": c5,
         "trace_variants": {"closest_full_hit_other_bvh_mrays": round(n_rays / ms_other / 1e3, 1),
                            "any_hit_ids_mrays": round(n_rays / ms_any / 1e3, 1), "hit_fraction": round(hit_fraction, 4)},
     }
@@ -296,6 +302,57 @@ def run_ours(args):
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def build_c5(eng, nx=5000, nz=5000, reps=5):
+    """BASELINE config C5: 50 M-triangle animated height field, full rebuild vs RR_BUILD_OPERATION_UPDATE per frame (mesh made
+    on the device, builds through rrCmdBuildGeometry, CUDA events); algorithmic bytes per triangle as in DESIGN.md section 4."""
+    import torch
+    from radeonrays_sdk_b200 import api
+    from radeonrays_sdk_b200.host import Geometry, _dev_bytes
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from bench_build import heightfield_device, REFIT_BYTES_PER_TRI
+    ctx, dev = eng.ctx, eng.device
+    pos, idx = heightfield_device(nx, nz, 0.0, dev)
+    n = idx.shape[0]
+    g = Geometry()
+    g.engine, g.triangle_count, g.vertex_count, g.vertex_stride = eng, n, pos.shape[0], 12
+    g.d_vertices, g.d_indices = pos.view(torch.uint8).reshape(-1), idx.view(torch.uint8).reshape(-1)
+    g.options = api.RRBuildOptions(api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD, None)
+    g.p_vertices, g.p_indices = ctx.tensor_ptr(g.d_vertices), ctx.tensor_ptr(g.d_indices)
+    g.input = ctx.geometry_input(g.p_vertices, g.vertex_count, 12, g.p_indices, n)
+    g.req = ctx.geometry_requirements(g.input, g.options)
+    g.d_temp, g.d_nodes = _dev_bytes(g.req.temporary_build_buffer_size, dev), _dev_bytes(g.req.result_buffer_size, dev)
+    g.p_temp, g.p_nodes = ctx.tensor_ptr(g.d_temp), ctx.tensor_ptr(g.d_nodes)
+
+    def timed(op):
+        cs = ctx.allocate_command_stream()
+        ctx.cmd_build_geometry(op, g.input, g.options, g.p_temp, g.p_nodes, cs)
+        ctx.release_event(ctx.submit(cs))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ctx.release_event(ctx.submit(cs))
+        e1.record()
+        torch.cuda.synchronize()
+        ctx.release_command_stream(cs)
+        return e0.elapsed_time(e1) / reps
+
+    ms_build = timed(api.RR_BUILD_OPERATION_BUILD)
+    pos2, _ = heightfield_device(nx, nz, 1.0, dev)
+    g.d_vertices.copy_(pos2.view(torch.uint8).reshape(-1))
+    ms_refit = timed(api.RR_BUILD_OPERATION_UPDATE)
+    peak, _ = measured_peak_gbs()
+    out = {"workload": f"C5: height field {nx}x{nz}, {n} triangles", "build_ms": round(ms_build, 4),
+           "build_mtris_per_s": round(n / ms_build / 1e3, 1), "build_gbs": round(BUILD_BYTES_PER_TRI * n / ms_build / 1e6, 1),
+           "build_roofline_frac": round(BUILD_BYTES_PER_TRI * n / ms_build / 1e6 / peak, 4), "refit_ms": round(ms_refit, 4),
+           "refit_mtris_per_s": round(n / ms_refit / 1e3, 1), "refit_gbs": round(REFIT_BYTES_PER_TRI * n / ms_refit / 1e6, 1),
+           "refit_roofline_frac": round(REFIT_BYTES_PER_TRI * n / ms_refit / 1e6 / peak, 4),
+           "algorithmic_bytes_per_triangle": {"build": BUILD_BYTES_PER_TRI, "refit": REFIT_BYTES_PER_TRI}}
+    del g, pos, idx, pos2
+    torch.cuda.empty_cache()
+    return out
 
 
 def host_threads():
@@ -372,6 +429,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bvh", default="quality", choices=["quality", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the 50 M-triangle build / refit leg (N=1 only; ~2 s, 9 GB)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="slices of the host batch pipelined through H2D / trace / D2H")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
