@@ -42,8 +42,11 @@ class Engine:
         self.ctx.destroy()
 
     # ---- geometry ----------------------------------------------------------------------------------------
-    def build_geometry(self, positions, indices, build_flags=api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD, vertex_stride=None):
-        """build_flags=None passes build_options == NULL (reference: no restructure, vlk/intersector.cpp:170)."""
+    def build_geometry(self, positions, indices, build_flags=api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD, vertex_stride=None,
+                       vertex_byte_offset=0):
+        """build_flags=None passes build_options == NULL (reference: no restructure, vlk/intersector.cpp:170).
+        vertex_byte_offset: the vertices start that many bytes into their device buffer (interop pointer + offset,
+        radeonrays_vlk.h:62-70), e.g. 4 for a buffer that is only 4-byte aligned."""
         g = Geometry()
         g.engine = self
         positions = np.ascontiguousarray(positions, np.float32)
@@ -52,11 +55,12 @@ class Engine:
         g.triangle_count = int(indices.shape[0])
         g.vertex_count = int(positions.shape[0])
         g.vertex_stride = int(vertex_stride or positions.shape[1] * 4)
-        g.d_vertices = _upload(positions, self.device)
+        g.vertex_byte_offset = int(vertex_byte_offset)
+        g.d_vertices = _upload(np.concatenate([np.zeros(g.vertex_byte_offset, np.uint8), positions.view(np.uint8).reshape(-1)]), self.device)
         g.d_indices = _upload(indices, self.device)
         g.options = api.RRBuildOptions(build_flags, None) if build_flags is not None else None
         ctx = self.ctx
-        g.p_vertices = ctx.tensor_ptr(g.d_vertices)
+        g.p_vertices = ctx.tensor_ptr(g.d_vertices, g.vertex_byte_offset)
         g.p_indices = ctx.tensor_ptr(g.d_indices)
         g.input = ctx.geometry_input(g.p_vertices, g.vertex_count, g.vertex_stride, g.p_indices, g.triangle_count,
                                      api.RR_INDEX_TYPE_UINT16 if index16 else api.RR_INDEX_TYPE_UINT32)
@@ -72,7 +76,7 @@ class Engine:
         self.ctx.run(lambda s: self.ctx.cmd_build_geometry(api.RR_BUILD_OPERATION_BUILD, g.input, g.options, g.p_temp, g.p_nodes, s))
 
     def update_geometry(self, g, positions):
-        g.d_vertices.copy_(_upload(np.ascontiguousarray(positions, np.float32), self.device))
+        g.d_vertices[getattr(g, "vertex_byte_offset", 0):].copy_(_upload(np.ascontiguousarray(positions, np.float32), self.device))
         self.ctx.run(lambda s: self.ctx.cmd_build_geometry(api.RR_BUILD_OPERATION_UPDATE, g.input, g.options, g.p_temp, g.p_nodes, s))
 
     # ---- scene ---------------------------------------------------------------------------------------------

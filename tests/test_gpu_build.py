@@ -157,6 +157,21 @@ def test_uint16_indices(engine, cornell):
     assert np.array_equal(got["prim_id"][ok], ref["prim_id"][ok])
 
 
+def test_vertex_buffer_at_4_byte_offset(engine):
+    """A vertex pointer that is only 4-byte aligned (interop pointer + offset): the 8+4-byte vertex loads of k_emit_leaves /
+    k_refit_leaves must fall back to scalar loads."""
+    rng = np.random.default_rng(44)
+    n_v, n = 30000, 600000                                 # large enough for the warp-cooperative refit path
+    pos = rng.random((n_v, 3), dtype=np.float32)
+    idx = rng.integers(0, n_v, (n, 3)).astype(np.uint32)
+    g = engine.build_geometry(pos, idx, vertex_byte_offset=4)
+    want, _, _ = O.build_blas(pos, idx)
+    assert_nodes_equal(g.nodes(), want, what="offset build")
+    moved = (pos + np.float32(0.25)).astype(np.float32)
+    engine.update_geometry(g, moved)
+    assert_nodes_equal(g.nodes(), O.refit(want, moved, idx), what="offset refit")
+
+
 def test_update_refit(engine, sponza):
     """hlbvh_test.h:445-493 UpdateTest: move every vertex by +10 in y, UPDATE, topology untouched."""
     pos, idx, _ = sponza
