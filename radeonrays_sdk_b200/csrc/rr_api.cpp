@@ -143,6 +143,10 @@ static inline DevicePtr*     D(RRDevicePtr p) { return reinterpret_cast<DevicePt
 static inline CommandStream* S(RRCommandStream s) { return reinterpret_cast<CommandStream*>(s); }
 static inline Event*         E(RREvent e) { return reinterpret_cast<Event*>(e); }
 
+// The kernels use 16- and 32-byte vector accesses: node arrays (geometry / scene buffers) must be 64-byte aligned, ray, hit
+// and temporary buffers 16-byte aligned (every cudaMalloc'ed buffer is; an interop pointer + offset may not be).
+static bool aligned_to(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
 static bool wants_restructure(const RRBuildOptions* o)
 {   // vlk/intersector.cpp:116-119,170
     return o && (o->build_flags & RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD) == 0;
@@ -249,6 +253,9 @@ RRError rrCmdBuildGeometry(RRContext context, RRBuildOperation build_operation, 
         if (RRError e = mesh_from_input(build_input, m)) return e;
         if (!m.vertices || !m.indices || !geometry_buffer) return RR_ERROR_INVALID_PARAMETER;
         Node*            nodes = reinterpret_cast<Node*>(D(geometry_buffer)->ptr());
+        if (!aligned_to(nodes, 64) || (temporary_buffer && !aligned_to(D(temporary_buffer)->ptr(), 16)) || !aligned_to(m.vertices, 4) ||
+            !aligned_to(m.indices, m.index16 ? 2 : 4))
+            return RR_ERROR_INVALID_PARAMETER;
         const DeviceInfo dev   = ctx->dev;
         if (build_operation == RR_BUILD_OPERATION_BUILD)
         {
@@ -314,6 +321,7 @@ RRError rrCmdBuildScene(RRContext context, const RRSceneBuildInput* build_input,
             throw std::runtime_error("scene build: buffer smaller than rrGetSceneBuildMemoryRequirements reported");
         void*            scratch = D(temporary_buffer)->ptr();
         void*            scene   = D(scene_buffer)->ptr();
+        if (!aligned_to(scene, 64) || !aligned_to(scratch, 16)) return RR_ERROR_INVALID_PARAMETER;
         const DeviceInfo dev     = ctx->dev;
         const bool       quirk   = ctx->reference_corner_quirk;
         S(command_stream)->commands.push_back([=](cudaStream_t s) {
@@ -366,6 +374,9 @@ RRError rrCmdIntersect(RRContext context, RRDevicePtr scene_buffer, RRIntersectQ
         a.query          = query;
         a.output         = query_output;
         a.first_found_tie_rule = ctx->first_found_tie_rule;
+        if (!aligned_to(a.bvh, 64) || !aligned_to(a.rays, 16) || !aligned_to(a.scratch, 16) ||
+            !aligned_to(a.hits, query_output == RR_INTERSECT_QUERY_OUTPUT_FULL_HIT ? 16 : 4) || !aligned_to(a.indirect_count, 4))
+            return RR_ERROR_INVALID_PARAMETER;
         if (ray_count && a.scratch_bytes < trace_scratch_size(ctx->dev, ray_count))
             throw std::runtime_error("intersect: scratch smaller than rrGetTraceMemoryRequirements reported");
         const DeviceInfo dev = ctx->dev;

@@ -128,3 +128,32 @@ def test_deep_stack_spill(engine):
     got = engine.intersect(g, rays)
     want, st = O.trace(nodes, rays, want_stats=True)
     assert_hits_equal(got, want, what="deep stack")
+
+
+def test_misaligned_buffers_are_rejected(engine, cornell):
+    """Interop pointer + offset (radeonrays_vlk.h:62-70 style): node arrays must be 64-byte aligned, rays / full hits /
+    scratch 16-byte aligned; anything else is RR_ERROR_INVALID_PARAMETER at record time, never a misaligned-address fault."""
+    import ctypes as C
+    import torch
+    pos, idx, _ = cornell
+    g = engine.build_geometry(pos, idx)
+    ctx = engine.ctx
+    rays = W.cornell_primary_rays(8)
+    rb = engine.make_ray_buffers(rays.shape[0])
+    cs = ctx.allocate_command_stream()
+
+    def intersect(scene, rays_p, hits_p, scratch_p):
+        return ctx.lib.rrCmdIntersect(ctx.handle, scene, api.RR_INTERSECT_QUERY_CLOSEST, rays_p, rays.shape[0], None,
+                                      api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, hits_p, scratch_p, cs)
+
+    assert intersect(g.p_nodes, rb.p_rays, rb.p_hits, rb.p_scratch) == api.RR_SUCCESS
+    assert intersect(ctx.tensor_ptr(g.d_nodes, 32), rb.p_rays, rb.p_hits, rb.p_scratch) == api.RR_ERROR_INVALID_PARAMETER
+    assert intersect(g.p_nodes, ctx.tensor_ptr(rb.d_rays, 8), rb.p_hits, rb.p_scratch) == api.RR_ERROR_INVALID_PARAMETER
+    assert intersect(g.p_nodes, rb.p_rays, ctx.tensor_ptr(rb.d_hits, 4), rb.p_scratch) == api.RR_ERROR_INVALID_PARAMETER
+    assert intersect(g.p_nodes, rb.p_rays, rb.p_hits, ctx.tensor_ptr(rb.d_scratch, 4)) == api.RR_ERROR_INVALID_PARAMETER
+    # a geometry buffer that is not 64-byte aligned is rejected by the build as well
+    spare = torch.empty(g.req.result_buffer_size + 64, dtype=torch.uint8, device=engine.device)
+    rc = ctx.lib.rrCmdBuildGeometry(ctx.handle, api.RR_BUILD_OPERATION_BUILD, C.byref(g.input), C.byref(g.options), g.p_temp,
+                                    ctx.tensor_ptr(spare, 16), cs)
+    assert rc == api.RR_ERROR_INVALID_PARAMETER
+    ctx.release_command_stream(cs)
