@@ -223,6 +223,10 @@ struct EmitParams
     uint32_t        n;
     Node*           nodes;
     uint32_t*       lists;   // per 512-leaf window: count + up to kListSlots left ends of the subtrees k_emit_window left over
+    uint8_t*        deltas;  // [n] delta(j, j+1) per sorted leaf in the geometry buffer's tail: written by a build, read by a refit
+    uint32_t*       refs_tail;   // [n] sorted primitive ids kept in the tail (mesh builds)
+    uint32_t*       karras;      // tail header word: 1 while the tree is Karras-numbered (cleared by the treelet restructuring)
+    bool            from_tail;   // refit: codes == nullptr, deltas / refs come from the tail; run only if *karras == 1
     bool            tma;     // k_emit_leaves stages node images in shared memory and stores them with TMA tensor copies
     uint32_t*       masks;             // [ceil(n/32)] per 32 leaves: left ends of the subtrees k_emit_leaves left over
     // mesh leaves
@@ -433,7 +437,7 @@ constexpr int kLeavesCtasPerSm = 3;  // 80 registers; 4 / 5 / 6 CTAs per SM meas
 // Mesh path: persistent warps with a three-deep software pipeline over their groups -- while group g is merged, the
 // vertex loads of g+1, the index loads of g+2 and the ref/code loads of g+3 are in flight, so the dependent chain
 // ref -> indices -> vertices (three DRAM latencies) never stalls the warp (it was 72 % of the stall samples).
-template <bool kScene>
+template <bool kScene, bool kFromTail>  // kFromTail: refit of a Karras-numbered tree from the deltas / ids kept in the geometry buffer's tail
 __global__ void __launch_bounds__(256, kLeavesCtasPerSm)
     k_emit_leaves(EmitParams p, const __grid_constant__ CUtensorMap tm_leaf, const __grid_constant__ CUtensorMap tm_node)
 {
@@ -481,6 +485,9 @@ __global__ void __launch_bounds__(256, kLeavesCtasPerSm)
         return;
     }
     if (g0 >= ngroups) return;
+    constexpr bool from_tail = kFromTail;
+    if (from_tail && *p.karras != 1u) return;
+    if (!from_tail && g0 == 0 && lane == 0) *p.karras = 1u;  // a fresh build is Karras-numbered (the treelet pass clears this)
     const float*    verts   = p.mesh.vertices;
     const size_t    vstride = p.mesh.stride_floats;
     // loads of a group that may lie past the end are clamped to the last leaf (results unused)
@@ -489,8 +496,14 @@ __global__ void __launch_bounds__(256, kLeavesCtasPerSm)
     auto load_codes = [&](int g) -> Codes {
         const int wb = g << 5;
         Codes k;
-        k.c    = p.codes[leaf_of(g)];
         k.edge = 0u;
+        if (from_tail)
+        {   // refit: delta(j, j+1) itself comes from the tail of the geometry buffer
+            k.c = p.deltas[leaf_of(g)];
+            if (lane == 0 && wb > 0 && wb < n) k.edge = p.deltas[wb - 1];
+            return k;
+        }
+        k.c = p.codes[leaf_of(g)];
         if (lane == 0 && wb > 0 && wb < n) k.edge = p.codes[wb - 1];
         if (lane == 31 && wb + 32 < n) k.edge = p.codes[wb + 32];
         return k;
@@ -547,8 +560,22 @@ __global__ void __launch_bounds__(256, kLeavesCtasPerSm)
         // deltas (0 outside the array: smaller than every real delta, 30-bit codes have clz >= 2)
         uint32_t cn = __shfl_down_sync(full, cod_c.c, 1);
         if (lane == 31) cn = cod_c.edge;
-        const int D = (valid && j + 1 < n) ? delta_of(cod_c.c, cn, j) : 0;
-        int       DL0 = (lane == 0 && wb > 0) ? delta_of(cod_c.edge, cod_c.c, wb - 1) : 0;
+        int D, DL0;
+        if (from_tail)
+        {
+            D   = (valid && j + 1 < n) ? (int)cod_c.c : 0;
+            DL0 = (lane == 0 && wb > 0) ? (int)cod_c.edge : 0;
+        }
+        else
+        {
+            D   = (valid && j + 1 < n) ? delta_of(cod_c.c, cn, j) : 0;
+            DL0 = (lane == 0 && wb > 0) ? delta_of(cod_c.edge, cod_c.c, wb - 1) : 0;
+            if (valid)
+            {   // what a refit needs to repeat this without the sorted codes
+                p.deltas[j]    = (uint8_t)D;
+                p.refs_tail[j] = ref_c;
+            }
+        }
         DL0 = __shfl_sync(full, DL0, 0);
         // lbvh_fit_aabb_mesh.comp:139-163
         const float3 lo = min3(min3(tri_c.v0, tri_c.v1), tri_c.v2), hi = max3(max3(tri_c.v0, tri_c.v1), tri_c.v2);
@@ -634,12 +661,13 @@ __global__ void __launch_bounds__(32 * kWindowWarps, 5) k_emit_window(EmitParams
     const int w = blockIdx.x * kWindowWarps + wi;
     const int b0 = w * kEmitWindow;
     if (b0 >= n) return;
+    if (p.from_tail && *p.karras != 1u) return;  // restructured tree: the generic refit kernels do the work
     const int cnt = min(kEmitWindow, n - b0), b1 = b0 + cnt - 1;
     uint8_t*  delta = s_delta[wi];
     for (int k = lane; k < cnt + 1; k += 32)
     {
         const int a = b0 - 1 + k;
-        delta[k] = (uint8_t)((a >= 0 && a + 1 < n) ? delta_of(p.codes[a], p.codes[a + 1], a) : 0);
+        delta[k] = (uint8_t)((a >= 0 && a + 1 < n) ? (p.from_tail ? (int)p.deltas[a] : delta_of(p.codes[a], p.codes[a + 1], a)) : 0);
     }
     auto delta_adj = [&](int a) -> int { return (int)delta[a + 1 - b0]; };   // a in [b0-1, b1]
     const int ngrp = (cnt + 31) >> 5;
@@ -742,6 +770,7 @@ __global__ void __launch_bounds__(32 * kUpperWarps) k_emit_upper(EmitParams p, c
     const int n = (int)p.n, leaf0 = n - 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t c0 = blockIdx.x * kUpperFan, nc = min((uint32_t)kUpperFan, num_in - c0);
     const int b1 = (int)min((uint64_t)n, (uint64_t)(c0 + nc) * leaves_per_in) - 1;  // last leaf of this window
+    if (p.from_tail && *p.karras != 1u) return;  // (uniform over the grid)
 
     // concatenate the lists of the children
     if (warp == 0)
@@ -766,7 +795,9 @@ __global__ void __launch_bounds__(32 * kUpperWarps) k_emit_upper(EmitParams p, c
     }
     __syncthreads();
 
-    auto delta_at = [&](int a) -> int { return (a >= 0 && a + 1 < n) ? delta_of(p.codes[a], p.codes[a + 1], a) : 0; };
+    auto delta_at = [&](int a) -> int {
+        return (a >= 0 && a + 1 < n) ? (p.from_tail ? (int)p.deltas[a] : delta_of(p.codes[a], p.codes[a + 1], a)) : 0;
+    };
     auto direct_store = [&](uint32_t idx, float4 q0, float4 q1, float4 q2, float4 q3) { st_node(p.nodes + idx, q0, q1, q2, q3); };
     bool prev_formed = true;
     for (int pass = 1; M > 1 && pass < kEmitMaxPasses; ++pass)
@@ -865,8 +896,10 @@ struct RefitLists
 template <bool kFromLeaves>
 __global__ void __launch_bounds__(256)
     k_refit(MeshDesc m, Node* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ in_count, const uint32_t* __restrict__ in_items,
-            uint32_t max_levels, uint32_t* __restrict__ out_count, uint32_t* __restrict__ out_items, uint32_t capacity)
+            uint32_t max_levels, uint32_t* __restrict__ out_count, uint32_t* __restrict__ out_items, uint32_t capacity,
+            const uint32_t* __restrict__ karras)
 {
+    if (karras && *karras == 1u) return;  // Karras-numbered tree: the emission kernels have refitted it already
     __shared__ uint32_t s_list[256];
     __shared__ uint32_t s_n, s_base;
     if (threadIdx.x == 0) s_n = 0;
@@ -972,8 +1005,10 @@ constexpr int kRefitSlots = 16;  // words per 32-leaf group handed from k_refit_
 // measured too: 3.8 ms against 3.1 ms at 50 M triangles -- the extra scattered word loads cost more than the rounds.)
 __global__ void __launch_bounds__(256, 4)  // 64 registers; 3 / 5 / 6 CTAs per SM: 3.84 / 3.88 / 4.58 ms refit at 50 M triangles against 3.60
     k_refit_leaves(MeshDesc m, Node* __restrict__ nodes, uint32_t n, uint32_t* __restrict__ slots, uint32_t* __restrict__ out_count,
-                   uint32_t* __restrict__ out_items, uint32_t capacity, const __grid_constant__ CUtensorMap tm_leaf, int tma)
+                   uint32_t* __restrict__ out_items, uint32_t capacity, const __grid_constant__ CUtensorMap tm_leaf, int tma,
+                   const uint32_t* __restrict__ karras)
 {
+    if (karras && *karras == 1u) return;
     // leaves leave through the TMA like in k_emit_leaves (one swizzled 2 KB block per group) when `tma`
     __shared__ __align__(1024) unsigned char s_stage[8][2048];
     unsigned char* st_leaf = s_stage[threadIdx.x >> 5];
@@ -1149,8 +1184,9 @@ __global__ void __launch_bounds__(256, 4)  // 64 registers; 3 / 5 / 6 CTAs per S
 // the rest (~2 % of the leaves: sibling outside the window) goes to the parity-rendezvous climb of k_refit<false>.
 __global__ void __launch_bounds__(256)
     k_refit_window(Node* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ slots, uint32_t* __restrict__ out_count,
-                   uint32_t* __restrict__ out_items, uint32_t capacity)
+                   uint32_t* __restrict__ out_items, uint32_t capacity, const uint32_t* __restrict__ karras)
 {
+    if (karras && *karras == 1u) return;
     __shared__ uint32_t s_list[8][2][16 * (kRefitSlots - 1) + 16];
     const uint32_t full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
@@ -1326,7 +1362,8 @@ int launch_emit_fit(const DeviceInfo& dev, cudaStream_t s, const EmitParams& p_i
     CUtensorMap tm_leaf{}, tm_node{};
     static const bool tma_allowed = [] { const char* e = std::getenv("RR_CUDA_EMIT_TMA"); return !e || std::atoi(e) != 0; }();
     p.tma = !kScene && tma_allowed && p.n >= 2 && node_tensor_map(&tm_leaf, p.nodes + (p.n - 1), p.n) && node_tensor_map(&tm_node, p.nodes, p.n - 1);
-    k_emit_leaves<kScene><<<ctas, 256, 0, s>>>(p, tm_leaf, tm_node);
+    if (p.from_tail) k_emit_leaves<kScene, true><<<ctas, 256, 0, s>>>(p, tm_leaf, tm_node);
+    else k_emit_leaves<kScene, false><<<ctas, 256, 0, s>>>(p, tm_leaf, tm_node);
     if (p.n <= 32) return 1;  // the whole tree was inside one group
     k_emit_window<kScene><<<(windows + kWindowWarps - 1) / kWindowWarps, 32 * kWindowWarps, 0, s>>>(p);
     int launches = 2;
@@ -1390,7 +1427,12 @@ BlasLayout blas_layout(uint32_t n, bool restructure)
     L.treelet_off  = 0;
     L.treelet_size = restructure ? treelet_scratch_size(n) : 0;
     L.scratch_total = std::max(off, L.treelet_size);
-    L.result_total  = sizeof(Node) * (2 * (size_t)n - 1);
+    // geometry buffer: VkBvhNode[2N-1], then the private tail (header | deltas | sorted primitive ids) a refit re-emits from
+    size_t roff = align_up(sizeof(Node) * (2 * (size_t)n - 1), 256);
+    L.tail_off        = roff; roff += 256;
+    L.tail_deltas_off = roff; roff += align_up((size_t)n, 256);
+    L.tail_refs_off   = roff; roff += align_up(sizeof(uint32_t) * (size_t)n, 256);
+    L.result_total    = roff;
     return L;
 }
 
@@ -1423,35 +1465,69 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
     p.codes = sorted_codes; p.refs = sorted_refs; p.n = n; p.nodes = nodes; p.mesh = mesh;
     p.lists = reinterpret_cast<uint32_t*>(sc + L.lists_off);
     p.masks = reinterpret_cast<uint32_t*>(sc + L.sort_off + L.sort.tmp_vals_off);  // the sort's ping-pong buffer is dead now
+    char* geom  = reinterpret_cast<char*>(nodes);
+    p.karras    = reinterpret_cast<uint32_t*>(geom + L.tail_off);
+    p.deltas    = reinterpret_cast<uint8_t*>(geom + L.tail_deltas_off);
+    p.refs_tail = reinterpret_cast<uint32_t*>(geom + L.tail_refs_off);
     *dev.launches += launch_emit_fit<false>(dev, s, p);
     RR_CUDA_CHECK(cudaGetLastError());
-    if (restructure) restructure_blas(dev, s, nodes, n, scratch);
+    if (restructure)
+    {   // the treelet pass renumbers nothing but re-links nodes: the tree is no longer the Karras tree of the stored deltas
+        restructure_blas(dev, s, nodes, n, scratch);
+        RR_CUDA_CHECK(cudaMemsetAsync(p.karras, 0, sizeof(uint32_t), s));
+    }
 }
 
 // Update scratch: [256 B: the two list counters | list A 4 x capacity | list B 4 x capacity], capacity = n/4 + 256:
 // a hand-over after k levels implies a finished subtree of >= k+1 leaves, so stage 1 (3 levels) emits <= n/4 entries.
-constexpr uint32_t kRefitWarpPathMin = 500000u;  // triangles from which stage 1 / 2 are the warp-cooperative kernels
+constexpr uint32_t kRefitWarpPathMin = 500000u;  // triangles from which the generic stages 1 / 2 are the warp-cooperative kernels
+// Scratch of the re-emission path: [256 B | one mask per 32 leaves | per-window lists], as in the build.
+static size_t reemit_scratch_size(uint32_t n) { return 256 + align_up(sizeof(uint32_t) * (((size_t)n + 31) / 32), 256) + align_up(emit_list_bytes(n), 256); }
 size_t update_scratch_size(uint32_t n)
 {
     const size_t cap = (size_t)n / 4 + 256;
+    size_t generic;
     if (n >= kRefitWarpPathMin)  // counters | stage-3 list | 16 words per 32-leaf group between k_refit_leaves and k_refit_window
-        return 256 + align_up(sizeof(uint32_t) * cap, 256) + align_up(sizeof(uint32_t) * kRefitSlots * (((size_t)n + 31) / 32), 256);
-    return 256 + 2 * align_up(sizeof(uint32_t) * cap, 256);
+        generic = 256 + align_up(sizeof(uint32_t) * cap, 256) + align_up(sizeof(uint32_t) * kRefitSlots * (((size_t)n + 31) / 32), 256);
+    else
+        generic = 256 + 2 * align_up(sizeof(uint32_t) * cap, 256);
+    return std::max(generic, reemit_scratch_size(n));
 }
 
+// RR_BUILD_OPERATION_UPDATE.  Two paths, chosen ON THE DEVICE by the header word of the geometry buffer's tail, so that a BLAS
+// stays self-describing when it is copied or broadcast:
+//  * Karras-numbered tree (fast build): the closed-form emission kernels of the build run again from the deltas and sorted
+//    primitive ids kept in the tail -- same topology by construction, every node rewritten whole, no atomics;
+//  * restructured tree (quality build): the generic staged refit (sibling pairing by shuffles, then the parity rendezvous).
+// Both sets of kernels are launched; the set that does not apply returns at once.
 void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, Node* nodes, void* scratch, size_t scratch_bytes)
 {
     const uint32_t n = mesh.triangle_count;
     if (n == 0) return;
-    const uint32_t kUnbounded = 0xFFFFFFFFu;
-    if (n < 4096 || !scratch || scratch_bytes < update_scratch_size(n))
-    {   // small mesh, or a client that passes no temporary buffer for updates (the Vulkan backend reports 0 bytes)
-        k_refit<true><<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n, nullptr, nullptr, kUnbounded, nullptr, nullptr, 0);
+    const uint32_t   kUnbounded = 0xFFFFFFFFu;
+    const BlasLayout BL = blas_layout(n, false);
+    char*            geom = reinterpret_cast<char*>(nodes);
+    uint32_t*        karras = reinterpret_cast<uint32_t*>(geom + BL.tail_off);
+    if (!scratch || scratch_bytes < update_scratch_size(n))
+    {   // a client that passes no temporary buffer for updates (the Vulkan backend reports 0 bytes): one generic kernel
+        k_refit<true><<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n, nullptr, nullptr, kUnbounded, nullptr, nullptr, 0, nullptr);
         ++*dev.launches;
         RR_CUDA_CHECK(cudaGetLastError());
         return;
     }
-    char*          sc  = (char*)scratch;
+    char* sc = (char*)scratch;
+    {   // re-emission (runs only while *karras == 1)
+        EmitParams p{};
+        p.codes = nullptr; p.n = n; p.nodes = nodes; p.mesh = mesh;
+        p.karras    = karras;
+        p.deltas    = reinterpret_cast<uint8_t*>(geom + BL.tail_deltas_off);
+        p.refs_tail = reinterpret_cast<uint32_t*>(geom + BL.tail_refs_off);
+        p.refs      = p.refs_tail;
+        p.from_tail = true;
+        p.masks = reinterpret_cast<uint32_t*>(sc + 256);
+        p.lists = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (((size_t)n + 31) / 32), 256));
+        *dev.launches += launch_emit_fit<false>(dev, s, p);
+    }
     const uint32_t cap = n / 4 + 256;
     RefitLists L;
     L.count_a = reinterpret_cast<uint32_t*>(sc);
@@ -1459,8 +1535,14 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
     L.items_a = reinterpret_cast<uint32_t*>(sc + 256);
     L.items_b = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (size_t)cap, 256));
     L.capacity = cap;
+    // (the generic path reuses the scratch of the re-emission: only one of the two is active)
     RR_CUDA_CHECK(cudaMemsetAsync(sc, 0, 8, s));
-    if (n >= kRefitWarpPathMin)
+    if (n < 4096)
+    {
+        k_refit<true><<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n, nullptr, nullptr, kUnbounded, nullptr, nullptr, 0, karras);
+        ++*dev.launches;
+    }
+    else if (n >= kRefitWarpPathMin)
     {   // large meshes: warp-cooperative stages 1 (per 32 leaves) and 2 (per 512-leaf window), then the parity-rendezvous climb
         // for the ~2 % that is left.  For small ones the pipeline prologue of the persistent kernel costs more than it hides
         // (Sponza, 262 k triangles: 0.150 against 0.133 ms).
@@ -1468,21 +1550,22 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
         CUtensorMap tm_leaf{};
         const int   tma = node_tensor_map(&tm_leaf, nodes + (n - 1), n) ? 1 : 0;
         k_refit_leaves<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)dev.sm_count * 4u), 256, 0, s>>>(mesh, nodes, n, slots, L.count_a, L.items_a,
-                                                                                                   cap, tm_leaf, tma);
+                                                                                                   cap, tm_leaf, tma, karras);
         const uint32_t windows = (n + kEmitWindow - 1) / kEmitWindow;
-        k_refit_window<<<(windows + 7) / 8, 256, 0, s>>>(nodes, n, slots, L.count_a, L.items_a, cap);
+        k_refit_window<<<(windows + 7) / 8, 256, 0, s>>>(nodes, n, slots, L.count_a, L.items_a, cap, karras);
         const uint32_t grid3 = std::min<uint32_t>((cap + 255) / 256, (uint32_t)dev.sm_count * 32u);
-        k_refit<false><<<grid3, 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, kUnbounded, nullptr, nullptr, cap);
+        k_refit<false><<<grid3, 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, kUnbounded, nullptr, nullptr, cap, karras);
+        *dev.launches += 3;
     }
     else
     {
-        k_refit<true><<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n, nullptr, nullptr, 3u, L.count_a, L.items_a, cap);
+        k_refit<true><<<(n + 255) / 256, 256, 0, s>>>(mesh, nodes, n, nullptr, nullptr, 3u, L.count_a, L.items_a, cap, karras);
         const uint32_t grid2 = std::min<uint32_t>((cap + 255) / 256, (uint32_t)dev.sm_count * 64u);
-        k_refit<false><<<grid2, 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, 6u, L.count_b, L.items_b, cap);
+        k_refit<false><<<grid2, 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, 6u, L.count_b, L.items_b, cap, karras);
         const uint32_t grid3 = std::min<uint32_t>((cap / 64 + 255) / 256 + 1, (uint32_t)dev.sm_count * 16u);
-        k_refit<false><<<grid3, 256, 0, s>>>(mesh, nodes, n, L.count_b, L.items_b, kUnbounded, nullptr, nullptr, cap);
+        k_refit<false><<<grid3, 256, 0, s>>>(mesh, nodes, n, L.count_b, L.items_b, kUnbounded, nullptr, nullptr, cap, karras);
+        *dev.launches += 3;
     }
-    *dev.launches += 3;
     RR_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -112,6 +112,10 @@ struct BlasLayout
     size_t     treelet_off = 0, treelet_size = 0;
     SortLayout sort;
     size_t     scratch_total = 0, result_total = 0;
+    // private tail of the geometry buffer, after the VkBvhNode[2N-1] array: what a refit needs to re-run the closed-form
+    // emission without the sorted codes -- [256 B header: word 0 = 1 while the tree is Karras-numbered | delta(j, j+1) per
+    // sorted leaf, 1 B | primitive id per sorted leaf, 4 B]
+    size_t     tail_off = 0, tail_deltas_off = 0, tail_refs_off = 0;
 };
 BlasLayout blas_layout(uint32_t triangle_count, bool restructure);
 void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, const BlasLayout& L, void* scratch, Node* nodes,

@@ -71,7 +71,12 @@ struct Buffer
         CHECK_RR_CALL(rrGetDevicePtrFromCudaPtr(ctx, mem, 0, &ptr));
     }
     template <class T>
-    void upload(const std::vector<T>& v) { CHECK_CUDA(cudaMemcpy(mem, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+    void upload(const std::vector<T>& v)
+    {   // cudaMemcpy from pageable memory may return before the DMA has landed, and the library's command streams are
+        // non-blocking streams (no implicit ordering with the legacy stream): wait for the copy before anything is submitted
+        CHECK_CUDA(cudaMemcpy(mem, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        CHECK_CUDA(cudaDeviceSynchronize());
+    }
     template <class T>
     std::vector<T> download(size_t count) const
     {
@@ -134,6 +139,7 @@ struct BuiltGeometry
     {
         vertices.upload(pos);
         CHECK_CUDA(cudaMemcpy(indices.mem, idx, size_t(tri_count) * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CHECK_CUDA(cudaDeviceSynchronize());
         mesh.vertices         = vertices.ptr;
         mesh.vertex_count     = (uint32_t)(pos.size() / 3);
         mesh.vertex_stride    = 3 * sizeof(float);
