@@ -16,13 +16,15 @@ extern "C" {
 
 /* Byte offsets, inside the temporary build buffer of a geometry with `triangle_count` triangles, of the
  * intermediate arrays the build leaves behind: scene AABB (uint[8], ordered encoding, reference
- * lbvh_init_mesh.comp:61-77), unsorted Morton codes, sorted codes, sorted primitive refs (u32[N] each). */
+ * lbvh_init_mesh.comp:61-77), unsorted Morton codes, sorted codes (u32[N] each).  The sorted primitive refs (u32[N]) are kept in
+ * the GEOMETRY buffer, after the node array, where RR_BUILD_OPERATION_UPDATE reads them: sorted_refs_offset is an offset
+ * into the geometry buffer. */
 typedef struct
 {
     size_t scene_aabb_offset;
     size_t morton_codes_offset;
     size_t sorted_codes_offset;
-    size_t sorted_refs_offset;
+    size_t sorted_refs_offset;     /* into the geometry buffer (not the temporary buffer) */
     size_t sort_tmp_values_offset; /* ping-pong value buffer of the sort, dead once the sort has finished */
 } RRCudaBuildScratchLayout;
 RR_API RRError rrCudaDebugGetBuildScratchLayout(RRContext context, uint32_t triangle_count, RRCudaBuildScratchLayout* layout);

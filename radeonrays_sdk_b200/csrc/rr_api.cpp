@@ -580,7 +580,7 @@ RRError rrCudaDebugGetBuildScratchLayout(RRContext context, uint32_t triangle_co
     layout->scene_aabb_offset   = L.aabb_off;
     layout->morton_codes_offset = L.codes_off;
     layout->sorted_codes_offset = L.sorted_codes_off;
-    layout->sorted_refs_offset  = L.sorted_refs_off;
+    layout->sorted_refs_offset  = L.tail_refs_off;  // inside the GEOMETRY buffer
     layout->sort_tmp_values_offset = L.sort_off + L.sort.tmp_vals_off;
     return RR_SUCCESS;
 }

@@ -570,11 +570,7 @@ __global__ void __launch_bounds__(256, kLeavesCtasPerSm)
         {
             D   = (valid && j + 1 < n) ? delta_of(cod_c.c, cn, j) : 0;
             DL0 = (lane == 0 && wb > 0) ? delta_of(cod_c.edge, cod_c.c, wb - 1) : 0;
-            if (valid)
-            {   // what a refit needs to repeat this without the sorted codes
-                p.deltas[j]    = (uint8_t)D;
-                p.refs_tail[j] = ref_c;
-            }
+            if (valid) p.deltas[j] = (uint8_t)D;  // with the sorted ids (already in the tail) all a refit needs to repeat this
         }
         DL0 = __shfl_sync(full, DL0, 0);
         // lbvh_fit_aabb_mesh.comp:139-163
@@ -1421,7 +1417,7 @@ BlasLayout blas_layout(uint32_t n, bool restructure)
     off += 256 - 32;  // the scene AABB keeps a 256-byte line of its own
     L.codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.sorted_codes_off = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
-    L.sorted_refs_off  = off; off += align_up(sizeof(uint32_t) * (size_t)n, 256);
+    L.sorted_refs_off  = 0;  // the sorted primitive ids go straight into the geometry buffer's tail (tail_refs_off)
     L.sort_off = off; off += L.sort.total;
     L.lists_off = off; off += align_up(emit_list_bytes(n), 256);
     L.treelet_off  = 0;
@@ -1453,7 +1449,8 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
     uint32_t* g_aabb       = reinterpret_cast<uint32_t*>(sc + L.aabb_off);
     uint32_t* codes        = reinterpret_cast<uint32_t*>(sc + L.codes_off);
     uint32_t* sorted_codes = reinterpret_cast<uint32_t*>(sc + L.sorted_codes_off);
-    uint32_t* sorted_refs  = reinterpret_cast<uint32_t*>(sc + L.sorted_refs_off);
+    // the last sort pass writes the sorted primitive ids where a refit will look for them: the geometry buffer's tail
+    uint32_t* sorted_refs  = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(nodes) + L.tail_refs_off);
     void*     sort_scratch = sc + L.sort_off;
 
     reset_build_scratch(s, sc, L.aabb_off, L.sort, L.sort_off);

@@ -24,7 +24,7 @@ def _check_build(engine, pos, idx, flags=api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUIL
         codes = g.scratch_u32(L.morton_codes_offset, n)
         assert np.array_equal(codes, O.morton_codes(pos, idx, lo, hi)), "Morton codes must be bit-exact"
         assert np.array_equal(g.scratch_u32(L.sorted_codes_offset, n), sc), "sorted codes"
-        assert np.array_equal(g.scratch_u32(L.sorted_refs_offset, n), sr), "sorted primitive order (stable)"
+        assert np.array_equal(g.d_nodes[L.sorted_refs_offset: L.sorted_refs_offset + 4 * n].cpu().numpy().view(np.uint32), sr), "sorted primitive order (stable)"
     got = g.nodes()
     assert_nodes_equal(got, want)
     assert O.check_consistency(got)

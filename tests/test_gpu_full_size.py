@@ -90,7 +90,7 @@ def test_c5_large_build_and_refit(engine, nx, nz):
     engine.rebuild(g)
     L = engine.ctx.build_scratch_layout(n)
     codes = g.d_temp[L.sorted_codes_offset: L.sorted_codes_offset + 4 * n].view(torch.int32)
-    refs = g.d_temp[L.sorted_refs_offset: L.sorted_refs_offset + 4 * n].view(torch.int32)
+    refs = g.d_nodes[L.sorted_refs_offset: L.sorted_refs_offset + 4 * n].view(torch.int32)   # kept in the geometry buffer's tail
     assert bool((codes[1:] >= codes[:-1]).all()), "sorted Morton codes"
     ties = codes[1:] == codes[:-1]
     assert bool((refs[1:][ties] > refs[:-1][ties]).all()), "equal codes keep ascending primitive order (stable sort)"

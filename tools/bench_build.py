@@ -71,7 +71,7 @@ def main():
         # device-side sanity: sorted codes ascending, refs a permutation, root box == mesh bounds
         L = ctx.build_scratch_layout(n)
         sc = g.d_temp[L.sorted_codes_offset: L.sorted_codes_offset + 4 * n].view(torch.int32)
-        sr = g.d_temp[L.sorted_refs_offset: L.sorted_refs_offset + 4 * n].view(torch.int32)
+        sr = g.d_nodes[L.sorted_refs_offset: L.sorted_refs_offset + 4 * n].view(torch.int32)   # geometry buffer tail
         sorted_ok = bool((sc[1:] >= sc[:-1]).all().item())
         perm_ok = bool((torch.sort(sr.to(torch.int64)).values == torch.arange(n, device=dev)).all().item())
         root = g.d_nodes[:64].view(torch.float32).cpu().numpy()
