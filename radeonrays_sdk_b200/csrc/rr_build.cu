@@ -1468,11 +1468,7 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
     p.refs_tail = reinterpret_cast<uint32_t*>(geom + L.tail_refs_off);
     *dev.launches += launch_emit_fit<false>(dev, s, p);
     RR_CUDA_CHECK(cudaGetLastError());
-    if (restructure)
-    {   // the treelet pass renumbers nothing but re-links nodes: the tree is no longer the Karras tree of the stored deltas
-        restructure_blas(dev, s, nodes, n, scratch);
-        RR_CUDA_CHECK(cudaMemsetAsync(p.karras, 0, sizeof(uint32_t), s));
-    }
+    if (restructure) restructure_blas(dev, s, nodes, n, scratch);  // (clears the tail's header word: no longer the Karras tree)
 }
 
 // Update scratch: [256 B: the two list counters | list A 4 x capacity | list B 4 x capacity], capacity = n/4 + 256:

@@ -393,6 +393,9 @@ void restructure_blas(const DeviceInfo& dev, cudaStream_t s, Node* nodes, uint32
         k_restructure<<<(max_roots + kTreeletWarps - 1) / kTreeletWarps, kTreeletWarps * 32, 0, s>>>(nodes, n, counts, root_count, roots);
         *dev.launches += 2;
     }
+    // The nodes are re-linked: the tree is no longer the Karras tree of the deltas kept in the geometry buffer's tail, so an
+    // update must use the generic refit (header word of the tail, see update_blas).
+    RR_CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<char*>(nodes) + blas_layout(n, false).tail_off, 0, sizeof(uint32_t), s));
     RR_CUDA_CHECK(cudaGetLastError());
 }
 

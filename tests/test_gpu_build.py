@@ -198,6 +198,23 @@ def test_update_after_quality_build(engine, sponza):
     assert_nodes_equal(g.nodes(), O.refit(before, moved, idx))
 
 
+def test_update_after_debug_restructure(engine, sponza):
+    """hlbvh_test.h:350-420 drives RestructureHlBvh on an already built BVH; an update afterwards must take the generic refit
+    (the tree is no longer the Karras tree a re-emission would produce)."""
+    import torch
+    pos, idx, _ = sponza
+    g = engine.build_geometry(pos, idx)                       # fast build: Karras-numbered, tail header = 1
+    ctx = engine.ctx
+    scratch = torch.empty(g.req.temporary_build_buffer_size + 64 * idx.shape[0], dtype=torch.uint8, device=engine.device)
+    api.check(ctx.lib.rrCudaDebugRestructure(ctx.handle, g.p_nodes, idx.shape[0], ctx.tensor_ptr(scratch)))
+    want, _, _ = O.build_blas(pos, idx, restructure=True)
+    before = g.nodes()
+    assert_nodes_equal(before, want, what="restructured")
+    moved = (pos * np.float32(0.75)).astype(np.float32)
+    engine.update_geometry(g, moved)
+    assert_nodes_equal(g.nodes(), O.refit(before, moved, idx), what="refit after restructure")
+
+
 def test_heightfield_1m(engine):
     """A 1 M-triangle slice of config C5's animated height field: rebuild and refit agree with the oracle."""
     pos, idx = W.heightfield_mesh(1000, 500, t=0.0)
