@@ -270,6 +270,9 @@ RRError rrCmdBuildGeometry(RRContext context, RRBuildOperation build_operation, 
         }
         else
         {   // UPDATE: the temporary buffer is optional (the reference's Vulkan backend ignores it, vlk/intersector.cpp:176-204)
+            // the update reads the tail of the geometry buffer (rr_build.cu update_blas): the whole result buffer must be there
+            if (D(geometry_buffer)->bytes_available() < blas_layout(m.triangle_count, false).result_total)
+                throw std::runtime_error("geometry update: buffer smaller than rrGetGeometryBuildMemoryRequirements reported");
             void*        scratch       = temporary_buffer ? D(temporary_buffer)->ptr() : nullptr;
             const size_t scratch_bytes = temporary_buffer ? D(temporary_buffer)->bytes_available() : 0;
             S(command_stream)->commands.push_back([=](cudaStream_t s) { update_blas(dev, s, m, nodes, scratch, scratch_bytes); });
