@@ -740,12 +740,13 @@ __global__ void __launch_bounds__(32 * kWindowWarps, 5) k_emit_window(EmitParams
     for (int e = lane; e < min(M, kListSlots); e += 32) out[1 + e] = (uint32_t)left_end(e);
 }
 
-// ---- level 3 and above: one CTA per 32 windows of the level below, until one window is the whole tree ----------------------
+// ---- level 3 and above: one CTA per 16 windows of the level below, until one window is the whole tree ----------------------
 // Same passes as k_emit_window, with the groups of a pass spread over the warps of the CTA (a barrier between passes) and
 // the deltas taken from the sorted codes: a few hundred elements per CTA, a few thousand CTAs at the first of these levels
 // for 50 M triangles, one CTA at the last, which forms the root.  No rendezvous words, atomics or fences anywhere in the
 // emission: the build is deterministic down to the order of its memory writes within a node.
-constexpr int kUpperFan      = 32;
+constexpr int kUpperFan      = 16;  // windows of the level below per CTA (<= 32: one warp scans their counts); 16 halves the
+                                    // shared memory of a CTA against 32 (8 instead of 4 resident): 4.18 -> 4.12 ms at 50 M triangles
 constexpr int kUpperWarps    = 8;
 constexpr int kUpperMaxElems = kUpperFan * kListSlots;
 struct UpperSmem
@@ -753,7 +754,7 @@ struct UpperSmem
     uint32_t list[2][kUpperMaxElems + 1];          // left ends of the current elements, ascending; ping-pong
     uint32_t stage[kUpperMaxElems + 64];           // what each group of a pass leaves over, before compaction
     uint32_t group_off[kUpperMaxElems / 32 + 4];   // per group: count, then (after the scan) offset
-    uint32_t child_off[kUpperFan + 1];
+    uint32_t child_off[33];
 };
 
 template <bool kScene>
@@ -783,7 +784,7 @@ __global__ void __launch_bounds__(32 * kUpperWarps) k_emit_upper(EmitParams p, c
         if (lane == 31) S.child_off[32] = incl;
     }
     __syncthreads();
-    int M = (int)S.child_off[kUpperFan], cur = 0;
+    int M = (int)S.child_off[32], cur = 0;
     for (uint32_t c = warp; c < nc; c += kUpperWarps)
     {
         const uint32_t base = S.child_off[c], cn = S.child_off[c + 1] - base;
@@ -1369,7 +1370,7 @@ int launch_emit_fit(const DeviceInfo& dev, cudaStream_t s, const EmitParams& p_i
         RR_CUDA_CHECK(cudaFuncSetAttribute(k_emit_upper<kScene>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpperSmem)));
         attr_set = true;
     }
-    // upper levels: 32 windows of the level below per CTA, lists ping-pong between the two halves of the list area
+    // upper levels: kUpperFan windows of the level below per CTA, lists ping-pong between the two halves of the list area
     uint32_t  num = windows, leaves_per = (uint32_t)kEmitWindow;
     uint32_t* in  = p.lists;
     uint32_t* out = p.lists + emit_list_words(windows);
