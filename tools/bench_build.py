@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--sizes", default="1000x500,4000x1000,5000x5000")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--check", action="store_true", help="download the BVH and run the oracle's structural check")
+    ap.add_argument("--no-refit", action="store_true", help="time the build only")
     args = ap.parse_args()
     eng = Engine(0)
     ctx, dev = eng.ctx, eng.device
@@ -79,7 +80,7 @@ def main():
         box_ok = bool(np.array_equal(lo, pos.min(0).values.cpu().numpy()) and np.array_equal(hi, pos.max(0).values.cpu().numpy()))
         pos2, _ = heightfield_device(nx, nz, 1.0, dev)
         g.d_vertices.copy_(pos2.view(torch.uint8).reshape(-1))
-        ms_refit = timed(api.RR_BUILD_OPERATION_UPDATE)
+        ms_refit = timed(api.RR_BUILD_OPERATION_UPDATE) if not args.no_refit else float('nan')
         out = {"workload": f"height field {nx}x{nz}", "triangles": n, "build_ms": round(ms_build, 4), "build_mtris_per_s": round(n / ms_build / 1e3, 1),
                "build_gbs": round(BUILD_BYTES_PER_TRI * n / ms_build / 1e6, 1), "build_roofline_frac": round(BUILD_BYTES_PER_TRI * n / ms_build / 1e6 / peak, 4),
                "refit_ms": round(ms_refit, 4), "refit_mtris_per_s": round(n / ms_refit / 1e3, 1),
