@@ -2,12 +2,15 @@
 //
 // What the reference does in 45+ dispatches (vlk/hlbvh_builder.cpp:159-351: init, scene AABB, Morton,
 // 8 x (histogram, scan, scatter), emit hierarchy, fit) runs here as:
-//   2 memset nodes -> k_scene_aabb -> k_morton (+ digit histograms) -> 4 onesweep passes -> k_emit_fit
-// k_emit_fit fuses hierarchy emission and bottom-up fitting: every node's 64 bytes are written once.
-// It produces the SAME tree, node numbering (Karras: internal i in [0,N-1), leaf j at N-1+j, root 0) and
-// boxes as lbvh_emit_hierarchy_mesh.comp:170-217 + lbvh_fit_aabb_mesh.comp:122-205 -- see the proof
-// sketch at k_emit_fit.  All arithmetic that feeds Morton codes is plain IEEE binary32 (the library is
-// compiled with --fmad=false).
+//   3 memset nodes -> k_scene_aabb -> k_morton (+ digit histograms) -> 4 onesweep passes ->
+//   k_emit_leaves -> k_emit_window -> k_emit_upper x ceil(log16(N/512))
+// The k_emit_* kernels fuse hierarchy emission and bottom-up fitting in closed form (group_merge): every node's 64
+// bytes are written once, without atomics.  They produce the SAME tree, node numbering (Karras: internal i in [0,N-1),
+// leaf j at N-1+j, root 0) and boxes as lbvh_emit_hierarchy_mesh.comp:170-217 + lbvh_fit_aabb_mesh.comp:122-205 -- see
+// the comment above group_merge.  RR_BUILD_OPERATION_UPDATE re-runs them from the deltas and sorted ids kept in the
+// geometry buffer's tail (update_blas), or, for treelet-restructured trees, runs the generic staged refit (k_refit*).
+// All arithmetic that feeds Morton codes is plain IEEE binary32 (the library is compiled with --fmad=false; SURVEY.md
+// App. B2).
 //
 // Algorithmic HBM bytes per triangle (u32 indices, 12-B vertices): aabb 48 + morton 48 + code write 4 +
 // sort 60 (identity values: no ref write/read in pass 0) + emit/fit: codes 8, refs 4, gather 48, nodes 128.
