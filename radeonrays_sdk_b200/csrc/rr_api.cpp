@@ -83,6 +83,16 @@ struct CommandStream
     cudaStream_t stream   = nullptr;
     bool         external = false;
     std::vector<std::function<void(cudaStream_t)>> commands;
+    // A command stream that is submitted again and again (a renderer's per-frame build / update / intersect list) is captured
+    // into a CUDA graph on its second submit and replayed from then on: a Sponza-sized build is 11 kernels + 3 memsets of
+    // ~10 us each, so launch gaps are a fifth of it.  Streams that record host copies (scene builds) or wrap a client's
+    // stream are always replayed command by command.
+    bool            graphable         = true;
+    int             submits           = 0;
+    cudaGraphExec_t exec              = nullptr;
+    size_t          captured_commands = 0;
+    uint64_t        captured_launches = 0;
+    ~CommandStream() { if (exec) cudaGraphExecDestroy(exec); }
 };
 
 struct Context
@@ -327,6 +337,7 @@ RRError rrCmdBuildScene(RRContext context, const RRSceneBuildInput* build_input,
         if (!aligned_to(scene, 64) || !aligned_to(scratch, 16)) return RR_ERROR_INVALID_PARAMETER;
         const DeviceInfo dev     = ctx->dev;
         const bool       quirk   = ctx->reference_corner_quirk;
+        S(command_stream)->graphable = false;  // the instance descriptors are copied from pageable host memory
         S(command_stream)->commands.push_back([=](cudaStream_t s) {
             build_scene(dev, s, descs->data(), L, scratch, scene, quirk);
             // the pageable host vector is staged synchronously by cudaMemcpyAsync; `descs` stays alive with the closure
@@ -430,7 +441,43 @@ RRError rrSumbitCommandStream(RRContext context, RRCommandStream command_stream,
         RR_CUDA_CHECK(cudaSetDevice(ctx->dev.device));
         // GPU-side wait: satisfies both the Vulkan (CPU wait, vlk/device.cpp:229-232) and DX12 (queue wait) contracts.
         if (wait_event) RR_CUDA_CHECK(cudaStreamWaitEvent(cs->stream, E(wait_event)->ev, 0));
-        for (auto& cmd : cs->commands) cmd(cs->stream);
+        static const bool graphs = [] { const char* e = std::getenv("RR_CUDA_GRAPHS"); return !e || std::atoi(e) != 0; }();
+        ++cs->submits;
+        if (graphs && cs->graphable && !cs->external && cs->exec && cs->captured_commands == cs->commands.size())
+        {
+            RR_CUDA_CHECK(cudaGraphLaunch(cs->exec, cs->stream));
+            ctx->launches += cs->captured_launches;
+        }
+        else if (graphs && cs->graphable && !cs->external && cs->submits >= 2 && !cs->commands.empty())
+        {   // (re)capture: the closures issue exactly the work a plain submit would
+            if (cs->exec) { cudaGraphExecDestroy(cs->exec); cs->exec = nullptr; }
+            const uint64_t l0 = ctx->launches;
+            cudaGraph_t    graph = nullptr;
+            bool           ok = cudaStreamBeginCapture(cs->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok)
+            {
+                try { for (auto& cmd : cs->commands) cmd(cs->stream); }
+                catch (...) { ok = false; }
+                if (cudaStreamEndCapture(cs->stream, &graph) != cudaSuccess || !graph) ok = false;
+            }
+            if (ok && cudaGraphInstantiate(&cs->exec, graph, 0) != cudaSuccess) { ok = false; cs->exec = nullptr; }
+            if (graph) cudaGraphDestroy(graph);
+            if (ok)
+            {
+                cs->captured_commands = cs->commands.size();
+                cs->captured_launches = ctx->launches - l0;
+                RR_CUDA_CHECK(cudaGraphLaunch(cs->exec, cs->stream));
+            }
+            else
+            {   // not capturable: never try again, run the commands directly
+                (void)cudaGetLastError();
+                cs->graphable = false;
+                ctx->launches = l0;
+                for (auto& cmd : cs->commands) cmd(cs->stream);
+            }
+        }
+        else
+            for (auto& cmd : cs->commands) cmd(cs->stream);
         std::unique_ptr<Event> ev(new Event);
         RR_CUDA_CHECK(cudaEventCreateWithFlags(&ev->ev, cudaEventDisableTiming));
         RR_CUDA_CHECK(cudaEventRecord(ev->ev, cs->stream));
