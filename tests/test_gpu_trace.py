@@ -4,7 +4,7 @@ import pytest
 
 from oracle import binding as O
 from radeonrays_sdk_b200 import api, workloads as W
-from helpers import assert_hits_equal
+from helpers import assert_hits_equal, assert_nodes_equal
 
 pytestmark = pytest.mark.gpu
 
@@ -156,4 +156,51 @@ def test_misaligned_buffers_are_rejected(engine, cornell):
     rc = ctx.lib.rrCmdBuildGeometry(ctx.handle, api.RR_BUILD_OPERATION_BUILD, C.byref(g.input), C.byref(g.options), g.p_temp,
                                     ctx.tensor_ptr(spare, 16), cs)
     assert rc == api.RR_ERROR_INVALID_PARAMETER
+    ctx.release_command_stream(cs)
+
+
+def test_resubmitted_command_stream_is_replayed_as_a_graph(engine, sponza):
+    """A renderer's per-frame list -- update the BLAS, trace -- recorded once and submitted every frame: from the second
+    submit on the library replays it as a CUDA graph (rr_api.cpp rrSumbitCommandStream); every frame must see that frame's
+    vertices, and appending a command afterwards must re-capture."""
+    import torch
+    pos, idx, _ = sponza
+    g = engine.build_geometry(pos, idx)
+    ctx = engine.ctx
+    rays = W.sponza_primary_rays(160, 90)
+    rb = engine.make_ray_buffers(rays.shape[0])
+    rb.d_rays[: 32 * rays.shape[0]].copy_(torch.from_numpy(rays.view(np.uint8).reshape(-1)))
+    before = g.nodes()
+    cs = ctx.allocate_command_stream()
+    ctx.cmd_build_geometry(api.RR_BUILD_OPERATION_UPDATE, g.input, g.options, g.p_temp, g.p_nodes, cs)
+    ctx.cmd_intersect(g.p_nodes, api.RR_INTERSECT_QUERY_CLOSEST, rb.p_rays, rays.shape[0], None,
+                      api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, rb.p_hits, rb.p_scratch, cs)
+    l0 = ctx.launch_count()
+    per_submit = None
+    for frame in range(4):
+        moved = (pos + np.float32(0.5 * frame)).astype(np.float32)
+        g.d_vertices.copy_(torch.from_numpy(moved.view(np.uint8).reshape(-1)))
+        rb.d_hits.zero_()
+        torch.cuda.synchronize()
+        e = ctx.submit(cs)
+        ctx.wait(e)
+        ctx.release_event(e)
+        n_launch = ctx.launch_count() - l0
+        l0 = ctx.launch_count()
+        per_submit = per_submit or n_launch
+        assert n_launch == per_submit > 0                      # the replay accounts for the same kernels
+        want_nodes = O.refit(before, moved, idx)
+        assert_nodes_equal(g.nodes(), want_nodes, what=f"frame {frame}")
+        got = rb.d_hits[: 16 * rays.shape[0]].cpu().numpy().view(W.HIT_DTYPE)
+        assert_hits_equal(got, O.trace(want_nodes, rays, init=np.zeros(rays.shape[0], W.HIT_DTYPE)), what=f"frame {frame}")
+    # one more command: the stream is captured again, both traces run
+    ids = torch.zeros(rays.shape[0], dtype=torch.int32, device=engine.device)
+    ctx.cmd_intersect(g.p_nodes, api.RR_INTERSECT_QUERY_ANY, rb.p_rays, rays.shape[0], None,
+                      api.RR_INTERSECT_QUERY_OUTPUT_INSTANCE_ID, ctx.tensor_ptr(ids), rb.p_scratch, cs)
+    for _ in range(2):
+        ids.fill_(-2)
+        e = ctx.submit(cs)
+        ctx.wait(e)
+        ctx.release_event(e)
+        assert int((ids == -2).sum().item()) == 0
     ctx.release_command_stream(cs)
