@@ -295,11 +295,11 @@ __device__ __forceinline__ void trace_ray(const TraceParams& P, StackT& st, uint
                         if (kFullHit)
                         {
                             const float2 uv = barycentrics(ray, t, q0, q1, q2);
-                            reinterpret_cast<float4*>(P.hits)[gidx] =
-                                make_float4(uv.x, uv.y, __uint_as_float(kTwoLevel ? cur_inst : 0u), __uint_as_float(prim));
+                            __stcs(reinterpret_cast<float4*>(P.hits) + gidx,
+                                   make_float4(uv.x, uv.y, __uint_as_float(kTwoLevel ? cur_inst : 0u), __uint_as_float(prim)));
                         }
                         else
-                            reinterpret_cast<uint32_t*>(P.hits)[gidx] = kTwoLevel ? cur_inst : prim;
+                            __stcs(reinterpret_cast<uint32_t*>(P.hits) + gidx, kTwoLevel ? cur_inst : prim);
                         return;
                     }
                     closest      = t;
