@@ -227,7 +227,6 @@ struct EmitParams
     Node*           nodes;
     uint32_t*       lists;   // per 512-leaf window: count + up to kListSlots left ends of the subtrees k_emit_window left over
     uint8_t*        deltas;  // [n] delta(j, j+1) per sorted leaf in the geometry buffer's tail: written by a build, read by a refit
-    uint32_t*       refs_tail;   // [n] sorted primitive ids kept in the tail (mesh builds)
     uint32_t*       karras;      // tail header word: 1 while the tree is Karras-numbered (cleared by the treelet restructuring)
     bool            from_tail;   // refit: codes == nullptr, deltas / refs come from the tail; run only if *karras == 1
     bool            tma;     // k_emit_leaves stages node images in shared memory and stores them with TMA tensor copies
@@ -1469,7 +1468,6 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
     char* geom  = reinterpret_cast<char*>(nodes);
     p.karras    = reinterpret_cast<uint32_t*>(geom + L.tail_off);
     p.deltas    = reinterpret_cast<uint8_t*>(geom + L.tail_deltas_off);
-    p.refs_tail = reinterpret_cast<uint32_t*>(geom + L.tail_refs_off);
     *dev.launches += launch_emit_fit<false>(dev, s, p);
     RR_CUDA_CHECK(cudaGetLastError());
     if (restructure) restructure_blas(dev, s, nodes, n, scratch);  // (clears the tail's header word: no longer the Karras tree)
@@ -1518,8 +1516,7 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
         p.codes = nullptr; p.n = n; p.nodes = nodes; p.mesh = mesh;
         p.karras    = karras;
         p.deltas    = reinterpret_cast<uint8_t*>(geom + BL.tail_deltas_off);
-        p.refs_tail = reinterpret_cast<uint32_t*>(geom + BL.tail_refs_off);
-        p.refs      = p.refs_tail;
+        p.refs      = reinterpret_cast<const uint32_t*>(geom + BL.tail_refs_off);  // written there by the build's last sort pass
         p.from_tail = true;
         p.masks = reinterpret_cast<uint32_t*>(sc + 256);
         p.lists = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (((size_t)n + 31) / 32), 256));
