@@ -175,9 +175,16 @@ def num_threads():
     return int(lib().rro_num_threads())
 
 
-def ref_bvh_analyzer_trace(nodes, rays, repeats=1, workdir=None, want_hits=False, threads=None):
+BRUTE_DTYPE = np.dtype([("t", "<f4"), ("prim_id", "<u4"), ("count", "<u4"), ("pad", "<u4")])
+
+
+def ref_bvh_analyzer_trace(nodes, rays, repeats=1, workdir=None, want_hits=False, threads=None, want_brute=False,
+                           stock_schedule=False):
     """Run the compiled REFERENCE CPU tracer (oracle/_ref/bvh_analyzer_trace) on a node dump. Returns its JSON.
-    `threads` sets OMP_NUM_THREADS for the child (torchrun exports OMP_NUM_THREADS=1 to its ranks)."""
+    `threads` sets OMP_NUM_THREADS for the child (torchrun exports OMP_NUM_THREADS=1 to its ranks).
+    want_hits: res["hits"] = the bvh::Hit array BvhIntersect<2> returned (bvh_analyzer/bvh.h:226-319).
+    want_brute: res["brute"] = per ray the (t, prim) minimum and the count of accepted triangles from the reference's
+    Triangle::Intersect (bvh_analyzer/triangle.h:34-70) run over every triangle of the dump (O(rays x triangles))."""
     import json, tempfile
     exe = os.path.join(_HERE, "_ref", "bvh_analyzer_trace")
     if not os.path.exists(exe):
@@ -187,13 +194,58 @@ def ref_bvh_analyzer_trace(nodes, rays, repeats=1, workdir=None, want_hits=False
     nodes.tofile(os.path.join(d, "bvh.bin"))
     np.ascontiguousarray(rays, dtype=RAY_DTYPE).tofile(os.path.join(d, "rays.bin"))
     cmd = [exe, os.path.join(d, "bvh.bin"), str(n - 1), str(n), os.path.join(d, "rays.bin"), str(rays.shape[0]), str(repeats)]
-    if want_hits:
+    if want_hits or want_brute:
         cmd.append(os.path.join(d, "hits.bin"))
+    if want_brute:
+        cmd.append(os.path.join(d, "brute.bin"))
     env = dict(os.environ)
     if threads:
         env["OMP_NUM_THREADS"] = str(int(threads))
+    if stock_schedule:
+        env["RR_REF_STOCK_SCHEDULE"] = "1"
     out = subprocess.run(cmd, capture_output=True, text=True, env=env)
     res = json.loads(out.stdout.strip().splitlines()[-1])
-    if want_hits:
+    if want_hits or want_brute:
         res["hits"] = np.fromfile(os.path.join(d, "hits.bin"), dtype=HIT_DTYPE)
+    if want_brute:
+        res["brute"] = np.fromfile(os.path.join(d, "brute.bin"), dtype=BRUTE_DTYPE)
+    return res
+
+
+def write_bvh_analyzer_config(directory, nodes, rays, width, height):
+    """The on-disk input of the STOCK bvh_analyzer binary: VkBvhNode dump + RRRay dump + the 7-line text config
+    (bvh_analyzer/config.h:46-63: bvh path, type string, internal-node count, triangle count, rays path, width, height;
+    the reference writes the two dumps under DUMP_BVH, test/test_vk/basic_test.h:519-555).  Returns the config path."""
+    n = (nodes.shape[0] + 1) // 2
+    assert rays.shape[0] == width * height
+    bvh_path, ray_path, cfg = (os.path.join(directory, f) for f in ("bvh.bin", "rays.bin", "config.txt"))
+    np.ascontiguousarray(nodes, dtype=NODE_DTYPE).tofile(bvh_path)
+    np.ascontiguousarray(rays, dtype=RAY_DTYPE).tofile(ray_path)
+    with open(cfg, "w") as f:
+        f.write("\n".join([bvh_path, "vkbvh2", str(n - 1), str(n), ray_path, str(width), str(height)]) + "\n")
+    return cfg
+
+
+def ref_bvh_analyzer_stock(nodes, rays, width, height, threads=None):
+    """Run the UNMODIFIED reference binary (oracle/_ref/bvh_analyzer = bvh_analyzer/main.cpp) end to end on the 7-line config:
+    IsValid, SAH, the `#pragma omp parallel for` trace with its per-ray omp critical, two JPEG writes (bvh.h:78-121).
+    Returns {is_valid, sah, avg_primary_node_tests, avg_primary_aabb_tests, avg_primary_triangle_tests, wall_s}, or None
+    when the binary is absent."""
+    import tempfile, time
+    exe = os.path.join(_HERE, "_ref", "bvh_analyzer")
+    if not os.path.exists(exe):
+        return None
+    with tempfile.TemporaryDirectory() as d:
+        cfg = write_bvh_analyzer_config(d, nodes, rays, width, height)
+        env = dict(os.environ)
+        if threads:
+            env["OMP_NUM_THREADS"] = str(int(threads))
+        t0 = time.time()
+        out = subprocess.run([exe, cfg], capture_output=True, text=True, env=env, cwd=d)   # the JPEGs land in d
+        wall = time.time() - t0
+        res = {"wall_s": wall, "returncode": out.returncode, "wrote_jpegs": os.path.exists(os.path.join(d, "isect_result.jpg"))}
+    for line in out.stdout.splitlines():
+        k, _, v = line.partition(": ")
+        if k in ("is_valid", "sah", "avg_primary_node_tests", "avg_primary_aabb_tests", "avg_primary_triangle_tests"):
+            res[k] = bool(int(v)) if k == "is_valid" else float(v)
     return res

@@ -6,13 +6,16 @@
  * bench.py's cpu_baseline / --impl reference legs may load it; the shipped library
  * (radeonrays_sdk_b200/csrc) never links, calls or falls back to anything in oracle/.
  *
- * Parity status: the reference's own tests hold NO value-level golden vectors for this path
- * (SURVEY.md section 8c): they assert RR_SUCCESS, BVH parent/child/box consistency, sorted keys ==
- * std::sort and SAH_after <= SAH_before.  The oracle is therefore pinned (tests/test_oracle_*.py)
- * by (i) those same structural checks, (ii) the reference's bvh_analyzer compiled from
- * /root/reference into oracle/_ref (IsValid + its own triangle test on our VkBvhNode dump),
- * (iii) an order-independent brute-force intersector, and otherwise only by the shader text
- * each function cites.  Hit-level values are "parity unpinned" by reference tests.
+ * Parity status: PINNED at value level to reference code run here, for everything the reference's one compilable
+ * component (bvh_analyzer, built from /root/reference into oracle/_ref by oracle/Makefile) computes: the triangle test
+ * (triangle.h:34-70: closest t bit for bit, hit/miss masks, primitive ids on C1 at 1024 x 1024 and on C2 samples), its
+ * BVH2 tracer (bvh.h:226-319: ids on single-intersection and clipped rays, uv), its validator and SAH (bvh.h:130-223)
+ * and the stock binary on the 7-line config -- tests/test_reference_pin_cpu.py, tests/test_gpu_reference_pin.py.
+ * The reference's tests hold NO golden vectors for the rest: Morton codes, sorted order, Karras
+ * topology, treelet output and TLAS are pinned by the structural assertions the reference's tests make (BVH
+ * consistency, sorted == std::sort, SAH_after <= SAH_before), by bvh_analyzer accepting the dump, and otherwise by the
+ * shader text each function cites; those rows stay "unpinned by reference values" because the Vulkan library cannot
+ * be compiled here (no Vulkan SDK, glslang or spdlog).
  *
  * Arithmetic contract: IEEE-754 binary32, round to nearest even, no FMA
  * contraction except where the GLSL writes fma() (compile with -ffp-contract=off).

@@ -2,7 +2,7 @@
 //
 // Layering (the analogue of the reference's base/ + vlk/ split):
 //   rr_api.cpp      C ABI shim: null checks -> RR_ERROR_INVALID_PARAMETER, exceptions -> RR_ERROR_INTERNAL
-//   rr_runtime.cpp  context / command stream / event / device pointer objects over the CUDA runtime
+//                   + context / command stream / event / device pointer objects over the CUDA runtime
 //   rr_build.cu     HLBVH build + refit + TLAS kernels and their launch sequences
 //   rr_sort.cu      onesweep LSD radix sort (stable key-value)
 //   rr_treelet.cu   treelet restructuring

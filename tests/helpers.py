@@ -28,3 +28,57 @@ def assert_hits_equal(got, want, rel_uv=1e-6, what="hits"):
     # untouched-on-miss semantics: uv / prim_id of missed rays keep whatever was there before (isect.comp:238-245)
     assert np.array_equal(got["prim_id"][~ok], want["prim_id"][~ok]), f"{what}: miss must not touch prim_id"
     assert np.array_equal(got["uv"][~ok].view(np.uint32), want["uv"][~ok].view(np.uint32)), f"{what}: miss must not touch uv"
+
+
+def pow2_scaled_rays(rays, max_shift=12):
+    """Rays whose direction components all have magnitude >= 1, made from `rays` by multiplying each direction by a power
+    of two (and dividing min_t / max_t by it): binary32 arithmetic scales exactly, so the hit triangle, uv and t * 2^m are
+    unchanged bit for bit.  Needed to compare with the reference's bvh_analyzer: its safe reciprocal calls an unqualified
+    `abs` (bvh_analyzer/float3.h:164-166) which g++ resolves to the INTEGER overload, so any |component| < 1 is treated as
+    zero and the ray's slab tests go wrong; with every |component| >= 1 its rcp is the shader's safe_invdir
+    (common.h:166-183).  Rays with a zero component (or needing more than max_shift doublings) are dropped.
+    -> (scaled rays, indices of the kept rays)"""
+    d = rays["direction"]
+    a = np.abs(d).min(1)
+    ok = a > 0
+    m = np.zeros(rays.shape[0], np.int32)
+    m[ok] = np.maximum(0, np.ceil(-np.log2(a[ok].astype(np.float64)))).astype(np.int32)
+    ok &= m <= max_shift
+    r = rays[ok].copy()
+    s = np.exp2(m[ok]).astype(np.float32)
+    r["direction"] *= s[:, None]
+    r["min_t"] /= s
+    r["max_t"] /= s
+    assert (np.abs(r["direction"]).min(1) >= 1).all()
+    return r, np.nonzero(ok)[0]
+
+
+def assert_matches_reference_tracer(hits, ref, what, max_mask_mismatch=4):
+    """`hits` (ours: oracle or GPU, closest-hit FULL_HIT) against what the REFERENCE's bvh_analyzer produced on the same node
+    dump and rays (oracle.binding.ref_bvh_analyzer_trace(want_hits=True, want_brute=True)).
+
+    * ref["brute"]: the reference's Triangle::Intersect (triangle.h:34-70) over every triangle -- the set of accepted
+      triangles is traversal independent, so: hit/miss mask equal (up to `max_mask_mismatch` grazing rays lost by the slab
+      test); prim id equal on every ray we hit that has exactly one accepted triangle; prim id equal to the reference's (t, prim) minimum on all rays but the exact-t ties the BVH walk
+      resolves by visit order (counted, returned).
+    * ref["hits"]: BvhIntersect<2> (bvh.h:226-319) keeps the LAST accepted triangle in its own visit order and tests its boxes
+      with an unfused multiply-add, so: mask equal up to `max_mask_mismatch` grazing rays, prim equal wherever exactly one
+      triangle is accepted, and its Moeller-Trumbore (u, v) close to our recomputed barycentrics when the prim agrees."""
+    brute, rh = ref["brute"], ref["hits"]
+    ours_hit = hits["inst_id"] != O.INVALID
+    # a hit of ours is always a triangle the reference test accepts; the converse may fail on a few grazing rays whose triangle
+    # lies in a face of a flat box the slab test (common.h:150-164) rejects by one ulp -- the reference's own BVH walk loses them too
+    assert not np.any(ours_hit & (brute["count"] == 0)), f"{what}: hit on a ray the reference triangle test rejects everywhere"
+    lost = np.count_nonzero(~ours_hit & (brute["count"] > 0))
+    assert lost <= max_mask_mismatch, f"{what}: {lost} rays miss although the reference triangle test accepts a triangle"
+    one = ours_hit & (brute["count"] == 1)
+    assert np.array_equal(hits["prim_id"][one], brute["prim_id"][one]), f"{what}: prim id differs on single-intersection rays"
+    differs = ours_hit & (hits["prim_id"] != brute["prim_id"])
+    ref_hit = rh["inst_id"] != O.INVALID
+    assert np.count_nonzero(ref_hit != ours_hit) <= max_mask_mismatch, f"{what}: mask vs BvhIntersect differs on {np.count_nonzero(ref_hit != ours_hit)} rays"
+    both = one & ref_hit
+    assert np.array_equal(hits["prim_id"][both], rh["prim_id"][both]), f"{what}: prim id differs from BvhIntersect on single-intersection rays"
+    same = ours_hit & ref_hit & (hits["prim_id"] == rh["prim_id"])
+    duv = np.abs(hits["uv"][same].astype(np.float64) - rh["uv"][same].astype(np.float64))
+    assert duv.size and np.median(duv) < 1e-5 and duv.max() < 5e-2, f"{what}: uv vs reference (u, v): median {np.median(duv)}, max {duv.max()}"
+    return int(np.count_nonzero(differs)), int(np.count_nonzero(one)), int(np.count_nonzero(same))
