@@ -53,6 +53,16 @@ typedef enum
 } RRCudaOption;
 RR_API RRError rrCudaSetOption(RRContext context, RRCudaOption option, int value);
 
+/* A scene buffer is self-describing (a header at its start holds a magic word, the instance count and the offsets of its parts;
+ * rrCmdIntersect tells a scene from a geometry on the device), so it may be traced through any context of the same device, copied
+ * with a plain device-to-device copy, or broadcast to another GPU.  Its instance records hold the device addresses of the
+ * geometries they were built over: after copying a scene next to COPIES of its geometries (another GPU, another arena), record one
+ * rebind per geometry -- every instance that pointed at `old_geometry_address` (the address the geometry had when the scene was
+ * built, on whatever device) then points at `new_geometry`.  No reference counterpart (RadeonRays is single-GPU and keeps the
+ * scene description in host-side state keyed by the buffer, vlk/intersector.cpp:86,263,289-290). */
+RR_API RRError rrCudaCmdRebindSceneGeometry(RRContext context, RRDevicePtr scene_buffer, void* old_geometry_address,
+                                            RRDevicePtr new_geometry, RRCommandStream command_stream);
+
 /* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches evidence). */
 RR_API RRError rrCudaGetLaunchCount(RRContext context, uint64_t* launches);
 

@@ -99,6 +99,7 @@ SIGNATURES = {
     "rrGetCudaPtrFromDevicePtr": [_vp, _vp, C.POINTER(_vp)],
     "rrCudaSetOption": [_vp, C.c_int, C.c_int],
     "rrCudaGetLaunchCount": [_vp, C.POINTER(C.c_uint64)],
+    "rrCudaCmdRebindSceneGeometry": [_vp, _vp, _vp, _vp, _vp],
     # radeonrays_cuda_debug.h
     "rrCudaDebugGetBuildScratchLayout": [_vp, C.c_uint32, C.POINTER(RRCudaBuildScratchLayout)],
     "rrCudaDebugSortPairs": [_vp, _vp, _vp, _vp, _vp, C.c_uint32],
@@ -277,6 +278,10 @@ class Context:
     def cmd_intersect(self, scene_ptr, query, rays_ptr, ray_count, indirect_ptr, output, hits_ptr, scratch_ptr, stream):
         check(self.lib.rrCmdIntersect(self.handle, scene_ptr, query, rays_ptr, ray_count, indirect_ptr, output, hits_ptr,
                                       scratch_ptr, stream), "rrCmdIntersect")
+
+    def cmd_rebind_scene_geometry(self, scene_ptr, old_address, new_geometry_ptr, stream):
+        check(self.lib.rrCudaCmdRebindSceneGeometry(self.handle, scene_ptr, _vp(int(old_address)), new_geometry_ptr, stream),
+              "rrCudaCmdRebindSceneGeometry")
 
     # ---- options / debug -------------------------------------------------------------------------------------
     def set_option(self, option, value):

@@ -8,7 +8,6 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
-#include <map>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -104,7 +103,6 @@ struct Context
     uint64_t     launches   = 0;
     bool         first_found_tie_rule   = false;
     bool         reference_corner_quirk = false;
-    std::map<const void*, uint32_t> scenes;  // scene buffer address -> instance count (vlk/intersector.cpp:86,263)
     ~Context()
     {
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -275,7 +273,6 @@ RRError rrCmdBuildGeometry(RRContext context, RRBuildOperation build_operation, 
             if (D(temporary_buffer)->bytes_available() < L.scratch_total || D(geometry_buffer)->bytes_available() < L.result_total)
                 throw std::runtime_error("geometry build: buffer smaller than rrGetGeometryBuildMemoryRequirements reported");
             void* scratch = D(temporary_buffer)->ptr();
-            ctx->scenes.erase(nodes);
             S(command_stream)->commands.push_back([=](cudaStream_t s) { build_blas(dev, s, m, L, scratch, nodes, restructure); });
         }
         else
@@ -342,7 +339,6 @@ RRError rrCmdBuildScene(RRContext context, const RRSceneBuildInput* build_input,
             build_scene(dev, s, descs->data(), L, scratch, scene, quirk);
             // the pageable host vector is staged synchronously by cudaMemcpyAsync; `descs` stays alive with the closure
         });
-        ctx->scenes[scene] = n;
     }
     catch (...) { return map_exception(); }
     return RR_SUCCESS;
@@ -366,19 +362,10 @@ RRError rrCmdIntersect(RRContext context, RRDevicePtr scene_buffer, RRIntersectQ
     {
         Context*  ctx = C(context);
         TraceArgs a{};
-        char*     scene = D(scene_buffer)->ptr();
-        auto      it    = ctx->scenes.find(scene);
-        if (it != ctx->scenes.end())
-        {   // two level: the buffer was produced by rrCmdBuildScene (vlk/intersector.cpp:289-324)
-            const SceneLayout L = scene_layout(it->second);
-            a.bvh       = reinterpret_cast<const Node*>(scene + L.nodes_off);
-            a.instances = reinterpret_cast<const InstanceRecord*>(scene + L.records_off);
-        }
-        else
-        {
-            a.bvh       = reinterpret_cast<const Node*>(scene);
-            a.instances = nullptr;
-        }
+        // One level or two: the buffer says so itself (SceneHeader, rr_internal.h) and the kernels branch on it on the device, so
+        // a scene built through another context, copied to another buffer or built later in the same stream is traced correctly
+        // (the reference keys a host-side map by the buffer handle instead, vlk/intersector.cpp:289-324).
+        a.scene          = D(scene_buffer)->ptr();
         a.rays           = reinterpret_cast<const RRRay*>(D(rays)->ptr());
         a.ray_count      = ray_count;
         a.indirect_count = indirect_ray_count ? reinterpret_cast<const uint32_t*>(D(indirect_ray_count)->ptr()) : nullptr;
@@ -388,7 +375,7 @@ RRError rrCmdIntersect(RRContext context, RRDevicePtr scene_buffer, RRIntersectQ
         a.query          = query;
         a.output         = query_output;
         a.first_found_tie_rule = ctx->first_found_tie_rule;
-        if (!aligned_to(a.bvh, 64) || !aligned_to(a.rays, 16) || !aligned_to(a.scratch, 16) ||
+        if (!aligned_to(a.scene, 64) || !aligned_to(a.rays, 16) || !aligned_to(a.scratch, 16) ||
             !aligned_to(a.hits, query_output == RR_INTERSECT_QUERY_OUTPUT_FULL_HIT ? 16 : 4) || !aligned_to(a.indirect_count, 4))
             return RR_ERROR_INVALID_PARAMETER;
         if (ray_count && a.scratch_bytes < trace_scratch_size(ctx->dev, ray_count))
@@ -613,6 +600,22 @@ RRError rrCudaSetOption(RRContext context, RRCudaOption option, int value)
     case RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK: C(context)->reference_corner_quirk = value != 0; return RR_SUCCESS;
     default: return RR_ERROR_INVALID_PARAMETER;
     }
+}
+
+RRError rrCudaCmdRebindSceneGeometry(RRContext context, RRDevicePtr scene_buffer, void* old_geometry_address, RRDevicePtr new_geometry,
+                                     RRCommandStream command_stream)
+{
+    if (!context || !scene_buffer || !old_geometry_address || !new_geometry || !command_stream) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        const DeviceInfo dev   = C(context)->dev;
+        void*            scene = D(scene_buffer)->ptr();
+        const void*      neu   = D(new_geometry)->ptr();
+        if (!aligned_to(scene, 64) || !aligned_to(neu, 64)) return RR_ERROR_INVALID_PARAMETER;
+        S(command_stream)->commands.push_back([=](cudaStream_t s) { rebind_scene(dev, s, scene, old_geometry_address, neu); });
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
 }
 
 RRError rrCudaGetLaunchCount(RRContext context, uint64_t* launches)

@@ -1289,8 +1289,9 @@ __device__ __forceinline__ float3 transform_point(const float* m, float3 p)
 
 __global__ void __launch_bounds__(256)
     k_instance_boxes(const InstanceDesc* __restrict__ descs, uint32_t n, int corner_quirk, float4* __restrict__ boxes,
-                     uint32_t* __restrict__ g_aabb)
+                     uint32_t* __restrict__ g_aabb, SceneHeader* __restrict__ header, SceneHeader header_value)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *header = header_value;  // the scene buffer describes itself (rr_internal.h)
     OrderedBox sb;
     sb.init();
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -1563,7 +1564,7 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
     RR_CUDA_CHECK(cudaGetLastError());
 }
 
-// Scene buffer: [nodes (2n-1) x 64 | instance records n x 64 | forward transforms n x 48]
+// Scene buffer: [SceneHeader | nodes (2n-1) x 64 | instance records n x 64 | forward transforms n x 48]
 // (reference: [(2n-1) x 64 | 2n x 48], vlk/hlbvh_top_level_builder.cpp:378-381; the BLAS addresses that the
 // reference binds as a descriptor array live in the records here, so there is no 2048-instance cap).
 SceneLayout scene_layout(uint32_t n)
@@ -1572,6 +1573,7 @@ SceneLayout scene_layout(uint32_t n)
     L.n    = n;
     L.sort = sort_layout(n);
     size_t off = 0;
+    off += 256;  // SceneHeader (64 B) in a line of its own
     L.nodes_off   = off; off += align_up(sizeof(Node) * (2 * (size_t)(n ? n : 1) - 1), 256);
     L.records_off = off; off += align_up(sizeof(InstanceRecord) * (size_t)n, 256);
     L.fwd_off     = off; off += align_up(48 * (size_t)n, 256);
@@ -1607,7 +1609,11 @@ void build_scene(const DeviceInfo& dev, cudaStream_t s, const InstanceDesc* host
 
     RR_CUDA_CHECK(cudaMemcpyAsync(descs, host_descs, sizeof(InstanceDesc) * (size_t)n, cudaMemcpyHostToDevice, s));
     reset_build_scratch(s, sc, L.aabb_off, L.sort, L.sort_off);
-    k_instance_boxes<<<grid_for(dev, n, 256, 4), 256, 0, s>>>(descs, n, corner_quirk ? 1 : 0, boxes, g_aabb);
+    SceneHeader h{};
+    h.magic[0] = kSceneMagic0; h.magic[1] = kSceneMagic1; h.magic[2] = kSceneMagic2; h.magic[3] = kSceneMagic3;
+    h.version = kSceneVersion; h.instance_count = n;
+    h.nodes_off = L.nodes_off; h.records_off = L.records_off; h.fwd_off = L.fwd_off;
+    k_instance_boxes<<<grid_for(dev, n, 256, 4), 256, 0, s>>>(descs, n, corner_quirk ? 1 : 0, boxes, g_aabb, reinterpret_cast<SceneHeader*>(out), h);
     k_morton<true><<<grid_for(dev, n, 256, 4), 256, 0, s>>>(MeshDesc{}, boxes, n, g_aabb, codes, sort_hist_ptr(L.sort, sort_scratch));
     *dev.launches += 2;
     sort_pairs(dev, s, L.sort, sort_scratch, codes, nullptr, sorted_codes, sorted_refs);
@@ -1621,6 +1627,23 @@ void build_scene(const DeviceInfo& dev, cudaStream_t s, const InstanceDesc* host
     p.lists = reinterpret_cast<uint32_t*>(sc + L.lists_off);
     p.masks = reinterpret_cast<uint32_t*>(sc + L.sort_off + L.sort.tmp_vals_off);  // the sort's ping-pong buffer is dead now
     *dev.launches += launch_emit_fit<true>(dev, s, p);
+    RR_CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) k_rebind_scene(void* scene, const Node* old_blas, const Node* new_blas)
+{
+    const SceneHeader* h = reinterpret_cast<const SceneHeader*>(scene);
+    if (h->magic[0] != kSceneMagic0 || h->magic[1] != kSceneMagic1 || h->magic[2] != kSceneMagic2 || h->magic[3] != kSceneMagic3) return;
+    InstanceRecord* rec = reinterpret_cast<InstanceRecord*>(static_cast<char*>(scene) + h->records_off);
+    const uint32_t  n   = h->instance_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (rec[i].blas == old_blas) rec[i].blas = new_blas;
+}
+
+void rebind_scene(const DeviceInfo& dev, cudaStream_t s, void* scene, const void* old_blas, const void* new_blas)
+{
+    k_rebind_scene<<<dev.sm_count, 256, 0, s>>>(scene, static_cast<const Node*>(old_blas), static_cast<const Node*>(new_blas));
+    *dev.launches += 1;
     RR_CUDA_CHECK(cudaGetLastError());
 }
 

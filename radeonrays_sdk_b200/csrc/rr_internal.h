@@ -45,6 +45,25 @@ struct alignas(64) InstanceRecord
 };
 static_assert(sizeof(InstanceRecord) == 64, "instance record must be 64 bytes");
 
+// First 64 bytes of a scene (TLAS) buffer.  The reference keeps "this buffer is a scene with n instances" in a per-context map
+// keyed by the buffer handle (vlk/intersector.cpp:86,263,289-290); here the buffer says so itself, so that a scene built through
+// one context can be traced through another, copied, or broadcast to another GPU (SURVEY.md section 8b "Ownership").
+// rrCmdIntersect launches the one-level and the two-level kernels; each reads these words on the device and returns at once when
+// the buffer is not of its kind.  The magic cannot be the start of a BLAS: word 3 would be node 0's child0, which is a node index
+// or 0xFFFFFFFF, and words 0-2 would be box coordinates, which are never these NaN payloads.
+struct alignas(64) SceneHeader
+{
+    uint32_t magic[4];
+    uint32_t version;
+    uint32_t instance_count;
+    uint32_t pad0[2];
+    uint64_t nodes_off, records_off, fwd_off;  // byte offsets from the start of the buffer
+    uint64_t pad1;
+};
+static_assert(sizeof(SceneHeader) == 64, "scene header must be 64 bytes");
+constexpr uint32_t kSceneMagic0 = 0x7FC05252u, kSceneMagic1 = 0x7FC05343u, kSceneMagic2 = 0x7FC04E45u, kSceneMagic3 = 0xFFFFFFFCu;
+constexpr uint32_t kSceneVersion = 2;
+
 // Host-side instance description consumed at record time (vlk/intersector.cpp:40-45, 222-247).
 struct InstanceDesc
 {
@@ -127,7 +146,7 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
 struct SceneLayout
 {
     uint32_t   n = 0;
-    size_t     nodes_off = 0, records_off = 0, fwd_off = 0, result_total = 0;  // scene buffer
+    size_t     nodes_off = 0, records_off = 0, fwd_off = 0, result_total = 0;  // scene buffer (SceneHeader at offset 0)
     size_t     desc_off = 0, boxes_off = 0, aabb_off = 0, codes_off = 0, sorted_codes_off = 0, sorted_refs_off = 0,
                sort_off = 0, lists_off = 0, scratch_total = 0;  // temporary buffer
     SortLayout sort;
@@ -136,6 +155,9 @@ SceneLayout scene_layout(uint32_t instance_count);
 // descs: host array already staged into pinned memory by the caller; copied to scratch on the stream.
 void build_scene(const DeviceInfo& dev, cudaStream_t s, const InstanceDesc* host_descs, const SceneLayout& L, void* scratch,
                  void* scene, bool reference_corner_quirk);
+// Rewrites every instance record of `scene` that points at `old_blas` to `new_blas` (after a scene buffer built on another GPU, or
+// next to other BLAS addresses, has been copied here).  Reads the instance count from the scene header on the device.
+void rebind_scene(const DeviceInfo& dev, cudaStream_t s, void* scene, const void* old_blas, const void* new_blas);
 
 // ---- treelets (rr_treelet.cu) ---------------------------------------------------------------------------
 size_t treelet_scratch_size(uint32_t n);
@@ -144,8 +166,7 @@ void   restructure_blas(const DeviceInfo& dev, cudaStream_t s, Node* nodes, uint
 // ---- trace (rr_trace.cu) ----------------------------------------------------------------------------------
 struct TraceArgs
 {
-    const Node*           bvh;          // BLAS (one level) or TLAS nodes (two level)
-    const InstanceRecord* instances;    // nullptr => one level
+    const void*           scene;        // geometry buffer (BLAS: VkBvhNode[2N-1]) or scene buffer (SceneHeader first); told apart on the device
     const RRRay*          rays;
     uint32_t              ray_count;
     const uint32_t*       indirect_count;  // optional device counter

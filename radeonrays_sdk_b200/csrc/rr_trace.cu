@@ -213,9 +213,31 @@ struct TraceParams
     uint32_t*             overflow_count; // word 1: rays whose stack did not fit in shared memory
     uint32_t*             deep_ticket;    // word 2: chunk counter of the deep kernel
     uint32_t*             overflow_list;  // [ray_count] indices of those rays
+    uint32_t*             packet_ticket;  // word 3: packet counter of k_trace_packet
+    uint32_t*             chunk_count;    // word 4: 32-ray chunks k_trace_packet handed to the per-ray kernel
+    uint32_t*             chunk_list;     // [ceil(ray_count / 32)] their chunk indices; nullptr: k_trace walks all chunks itself
     int                   first_found;
     int                   force_generic;
 };
+
+// A geometry buffer starts with node 0, a scene buffer with a SceneHeader (rr_internal.h): every kernel checks on the device that
+// the buffer is of the kind it traverses and returns at once otherwise (rrCmdIntersect launches both kinds; the reference keeps a
+// host-side map keyed by the buffer instead, vlk/intersector.cpp:289-290).  For a scene, bvh / instances are taken from the header.
+template <bool kTwoLevel>
+__device__ __forceinline__ bool resolve_scene(TraceParams& P)
+{
+    const uint4 m     = __ldg(reinterpret_cast<const uint4*>(P.bvh));
+    const bool  scene = m.x == kSceneMagic0 && m.y == kSceneMagic1 && m.z == kSceneMagic2 && m.w == kSceneMagic3;
+    if (scene != kTwoLevel) return false;
+    if (kTwoLevel)
+    {
+        const char*        base = reinterpret_cast<const char*>(P.bvh);
+        const SceneHeader* h    = reinterpret_cast<const SceneHeader*>(base);
+        P.instances = reinterpret_cast<const InstanceRecord*>(base + h->records_off);
+        P.bvh       = reinterpret_cast<const Node*>(base + h->nodes_off);
+    }
+    return true;
+}
 
 // Leaving an instance: restore the world-space ray (isect_2l.comp:279-287) and pop again.
 #define RR_POP_NEXT()                                                         \
@@ -356,6 +378,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(Tra
 {
     constexpr int kEntries = kTwoLevel ? kSmemStack2 : kSmemStack1;
     __shared__ uint32_t s_stack[kEntries * kTraceThreads];
+    if (!resolve_scene<kTwoLevel>(P)) return;
     uint32_t count = P.ray_count;
     if (P.indirect) count = min(count, __ldg(P.indirect));  // isect.comp:98-103
     const uint32_t lane = threadIdx.x & 31;
@@ -364,7 +387,12 @@ __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(Tra
     while (true)
     {
         uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(P.ticket, 1u);
+        if (lane == 0)
+        {
+            chunk = atomicAdd(P.ticket, 1u);
+            // list mode: only the chunks the packet kernel declined (incoherent rays, deep trees)
+            if (P.chunk_list) chunk = chunk < *P.chunk_count ? P.chunk_list[chunk] : kInvalid;
+        }
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if ((uint64_t)chunk * 32 >= count) break;
         const uint32_t gidx  = chunk * 32 + lane;
@@ -395,6 +423,180 @@ __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(Tra
     }
 }
 
+
+// ---- packet traversal of coherent closest-hit rays ------------------------------------------------------------------------------
+// k_trace above is bound by the SM's L1 return path: every lane receives the 64 bytes of each node it visits, 4 bytes per lane per
+// clock per SM whatever the address pattern (tools/ubench/l1_broadcast.cu: a warp-uniform LDG.128 costs the same 4 clk as a
+// divergent one that hits one line; sm_100a has no global load into uniform registers).  What can be shared is the VISIT: when the
+// rays of a warp are coherent they walk almost the same nodes (C2: 56 internal nodes per ray, 73 in the union of 64 neighbouring
+// rays), so here a warp owns 64 consecutive rays -- two per lane, "slots" of 32 -- and ONE traversal: one node fetch, one stack
+// (in shared memory, warp uniform) and one descend / defer decision per node for all 64 rays; a lane still tests its own two rays
+// against both child boxes with the reference's arithmetic (slab<kOct>) and against each triangle (tri_test), and a child is
+// entered when any ray wants it.  Per 64 rays that is half the node bytes of two 32-ray warps, no divergence in the triangle test, and the
+// control flow amortised over two rays per lane.
+// Closest-hit only, and only under the default tie rule: a ray's result is the (t, prim) minimum over the triangles it accepts,
+// which does not depend on the visit order; every triangle a ray would reach on its own walk is reached here too because the
+// lane votes with the same box test against its own running closest t.  (Exact-t ties at the ulp level of the slab test can
+// resolve differently from k_trace; they equal the brute-force (t, prim) minimum more often, tests/test_gpu_trace.py counts them.)
+// ANY queries and RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND depend on the reference's visit order and stay on k_trace.
+// A packet whose 64 rays do not share a direction octant, or whose shared stack would overflow, is handed to k_trace through
+// the chunk list (two 32-ray chunks), which then runs in list mode right after this kernel.
+constexpr int      kPacketThreads = 128;
+constexpr int      kPacketStack   = 64;            // entries per warp; LBVH depth beyond that goes to k_trace / k_trace_deep
+
+template <bool kFullHit>
+__device__ __forceinline__ void write_closest(const TraceParams& P, uint32_t gidx, const float4& r0, const float4& r1, float closest,
+                                              uint32_t closest_addr, uint32_t closest_prim)
+{
+    if (closest_addr != kInvalid)
+    {
+        if (kFullHit)
+        {
+            RayState ray;
+            ray.o = v3(r0); ray.d = v3(r1);
+            const float4* np = reinterpret_cast<const float4*>(P.bvh + closest_addr);
+            const float2  uv = barycentrics(ray, closest, __ldg(np), __ldg(np + 1), __ldg(np + 2));
+            __stcs(reinterpret_cast<float4*>(P.hits) + gidx, make_float4(uv.x, uv.y, __uint_as_float(0u), __uint_as_float(closest_prim)));
+        }
+        else
+            __stcs(reinterpret_cast<uint32_t*>(P.hits) + gidx, closest_prim);
+    }
+    else
+    {   // miss: only the id word is written (isect.comp:238-245)
+        if (kFullHit) reinterpret_cast<uint32_t*>(P.hits)[4 * (size_t)gidx + 2] = kInvalid;
+        else reinterpret_cast<uint32_t*>(P.hits)[gidx] = kInvalid;
+    }
+}
+
+// One packet, start to finish.  Returns false when the shared stack overflowed (nothing has been written then).
+// The loop is written for issue slots (the kernel is issue bound, profiles/round2_summary.md): both slots are tested at every
+// node (their arithmetic interleaves), a lane without a ray carries closest = -FLT_MAX so that no test of it can pass, one
+// predicate per child ("any of my two rays wants it") feeds one VOTE.ANY, the near child is the one most lanes' slot-0 rays
+// enter first, and the stack is addressed through a 32-bit shared-memory address.
+template <bool kFullHit, int kOct>
+__device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stack_lo, const uint32_t (&gidx)[2], const bool (&valid)[2],
+                                             const float4 (&r0)[2], const float4 (&r1)[2], const RayState (&ray)[2])
+{
+    const float kNever = -3.402823466e+38f;
+    float    closest[2]      = {valid[0] ? r1[0].w : kNever, valid[1] ? r1[1].w : kNever};
+    uint32_t closest_addr[2] = {kInvalid, kInvalid}, closest_prim[2] = {kInvalid, kInvalid};
+    uint32_t sp  = stack_lo;                                   // shared-memory byte address of the next free entry
+    const uint32_t stack_hi = stack_lo + kPacketStack * 4;
+    uint32_t cur = 0;
+    while (true)
+    {
+        const float4* np = reinterpret_cast<const float4*>(P.bvh + cur);
+        float4 q0, q1, q2, q3;
+        ldg_half_node(np, q0, q1);
+        ldg_half_node(np + 2, q2, q3);
+        if (wbits(q0) != kInvalid)
+        {
+            float a0, a1, b0, b1, c0, c1, d0, d1;
+            slab<kOct>(q0, q1, ray[0], closest[0], r0[0].w, a0, a1);
+            slab<kOct>(q2, q3, ray[0], closest[0], r0[0].w, b0, b1);
+            slab<kOct>(q0, q1, ray[1], closest[1], r0[1].w, c0, c1);
+            slab<kOct>(q2, q3, ray[1], closest[1], r0[1].w, d0, d1);
+            const bool     any0  = __any_sync(0xffffffffu, a0 <= a1 || c0 <= c1);
+            const bool     any1  = __any_sync(0xffffffffu, b0 <= b1 || d0 <= d1);
+            const bool     first1 = __popc(__ballot_sync(0xffffffffu, b0 < a0)) > 16;  // majority of the slot-0 rays: child 1 is nearer
+            const bool     take1 = any1 && (!any0 || first1);
+            if (any0 && any1)
+            {   // defer the other child: one predicated store each instead of a select (the kernel is bound by the ALU pipe)
+                if (sp >= stack_hi) return false;
+                if (take1) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(wbits(q0)) : "memory");
+                else       asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(wbits(q1)) : "memory");
+                sp += 4;
+            }
+            if (any0 || any1)
+            {
+                cur = take1 ? wbits(q1) : wbits(q0);
+                continue;
+            }
+        }
+        else
+        {
+            const uint32_t prim = wbits(q1);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+            {
+                float t;
+                if (tri_test(ray[k], r0[k].w, q0, q1, q2, closest[k], t) && (t < closest[k] || (closest_addr[k] != kInvalid && prim < closest_prim[k])))
+                {   // tri_test accepted t <= closest: smaller t, or the same t and a lower primitive id
+                    closest[k]      = t;
+                    closest_addr[k] = cur;
+                    closest_prim[k] = prim;
+                }
+            }
+        }
+        if (sp == stack_lo) break;
+        sp -= 4;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(sp) : "memory");
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (valid[k]) write_closest<kFullHit>(P, gidx[k], r0[k], r1[k], closest[k], closest_addr[k], closest_prim[k]);
+    return true;
+}
+
+template <bool kFullHit>
+__global__ void __launch_bounds__(kPacketThreads, 7) k_trace_packet(TraceParams P)
+{
+    __shared__ uint32_t s_stack[(kPacketThreads / 32) * kPacketStack];
+    if (!resolve_scene<false>(P)) return;
+    uint32_t count = P.ray_count;
+    if (P.indirect) count = min(count, __ldg(P.indirect));
+    const uint32_t lane  = threadIdx.x & 31;
+    const uint32_t stack = (uint32_t)__cvta_generic_to_shared(s_stack + (threadIdx.x >> 5) * kPacketStack);
+    while (true)
+    {
+        uint32_t packet = 0;
+        if (lane == 0) packet = atomicAdd(P.packet_ticket, 1u);
+        packet = __shfl_sync(0xffffffffu, packet, 0);
+        if ((uint64_t)packet * 64 >= count) break;
+        uint32_t gidx[2];
+        bool     valid[2];
+        float4   r0[2], r1[2];
+        RayState ray[2];
+        int      oct[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+        {
+            gidx[k]  = packet * 64 + k * 32 + lane;
+            valid[k] = gidx[k] < count;
+            const uint32_t ridx = valid[k] ? gidx[k] : count - 1;
+            r0[k] = __ldcs(P.rays + 2 * (size_t)ridx);
+            r1[k] = __ldcs(P.rays + 2 * (size_t)ridx + 1);
+            ray[k].set(v3(r0[k]), v3(r1[k]));
+            oct[k] = ray[k].octant();
+        }
+        const uint32_t slots    = (uint64_t)packet * 64 + 32 < count ? 3u : 1u;  // the last packet may hold one chunk only
+        const int      oct0     = __shfl_sync(0xffffffffu, oct[0], 0);
+        const bool     coherent = oct0 != 8 && __all_sync(0xffffffffu, oct[0] == oct0 && oct[1] == oct0);
+        bool done = false;
+        if (coherent)
+        {
+            switch (oct0)
+            {
+            case 0: done = trace_packet<kFullHit, 0>(P, stack, gidx, valid, r0, r1, ray); break;
+            case 1: done = trace_packet<kFullHit, 1>(P, stack, gidx, valid, r0, r1, ray); break;
+            case 2: done = trace_packet<kFullHit, 2>(P, stack, gidx, valid, r0, r1, ray); break;
+            case 3: done = trace_packet<kFullHit, 3>(P, stack, gidx, valid, r0, r1, ray); break;
+            case 4: done = trace_packet<kFullHit, 4>(P, stack, gidx, valid, r0, r1, ray); break;
+            case 5: done = trace_packet<kFullHit, 5>(P, stack, gidx, valid, r0, r1, ray); break;
+            case 6: done = trace_packet<kFullHit, 6>(P, stack, gidx, valid, r0, r1, ray); break;
+            default: done = trace_packet<kFullHit, 7>(P, stack, gidx, valid, r0, r1, ray); break;
+            }
+        }
+        if (!done && lane == 0)
+        {   // hand both chunks to the per-ray kernel
+            const uint32_t n = slots == 3u ? 2u : 1u;
+            const uint32_t at = atomicAdd(P.chunk_count, n);
+            P.chunk_list[at] = packet * 2;
+            if (n == 2u) P.chunk_list[at + 1] = packet * 2 + 1;
+        }
+    }
+}
+
 // Second launch of every intersect: traces the (normally zero) rays whose deferred-node stack outgrew shared memory,
 // with the generic loop and a global-memory stack.  Exits at once when the list is empty.
 template <bool kAny, bool kFullHit, bool kTwoLevel>
@@ -402,6 +604,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_deep(TraceParams P)
 {
     const uint32_t count = *P.overflow_count;
     if (count == 0) return;
+    if (!resolve_scene<kTwoLevel>(P)) return;
     const uint32_t lane = threadIdx.x & 31;
     DeepStack st;
     st.base   = P.arena + (blockIdx.x * kTraceThreads + threadIdx.x);
@@ -446,14 +649,23 @@ void launch(const DeviceInfo& dev, cudaStream_t s, const TraceParams& P)
 }
 }  // namespace
 
-// Scratch: [256 B header: main ticket, overflow count, deep ticket | overflow list: 4 B per ray | deep-kernel stacks:
-// kDeepStack words for each of its thread slots].  The reference asks for 256 B per ray (vlk/geometry_trace.cpp:169).
+// Scratch: [256 B header: main ticket, overflow count, deep ticket, packet ticket, declined-chunk count | overflow list: 4 B per
+// ray | declined-chunk list: 4 B per 32 rays | deep-kernel stacks: kDeepStack words for each of its thread slots].  The reference
+// asks for 256 B per ray (vlk/geometry_trace.cpp:169).
 constexpr size_t kScratchHeader = 256;
 static size_t overflow_list_bytes(uint32_t ray_count) { return align_up(sizeof(uint32_t) * (size_t)ray_count, 256); }
+static size_t chunk_list_bytes(uint32_t ray_count) { return align_up(sizeof(uint32_t) * (((size_t)ray_count + 31) / 32 + 1), 256); }
 size_t trace_scratch_size(const DeviceInfo& dev, uint32_t ray_count)
 {
-    return kScratchHeader + overflow_list_bytes(ray_count) +
+    return kScratchHeader + overflow_list_bytes(ray_count) + chunk_list_bytes(ray_count) +
            (size_t)trace_grid(dev, ray_count, kDeepCtasPerSm) * kTraceThreads * kDeepStack * sizeof(uint32_t);
+}
+
+// Resident CTAs per SM of the packet kernel (RR_CUDA_PACKET_CTAS_PER_SM overrides it for tuning).
+static int packet_ctas_per_sm()
+{
+    static int env = [] { const char* e = std::getenv("RR_CUDA_PACKET_CTAS_PER_SM"); return e ? std::atoi(e) : 0; }();
+    return std::min(env > 0 ? env : 7, 16);
 }
 
 void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
@@ -461,25 +673,38 @@ void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
     if (a.ray_count == 0) return;
     if (a.scratch_bytes < trace_scratch_size(dev, a.ray_count)) throw std::runtime_error("trace scratch buffer too small");
     TraceParams P;
-    P.bvh = a.bvh; P.instances = a.instances; P.rays = reinterpret_cast<const float4*>(a.rays); P.ray_count = a.ray_count;
+    P.bvh = static_cast<const Node*>(a.scene); P.instances = nullptr; P.rays = reinterpret_cast<const float4*>(a.rays); P.ray_count = a.ray_count;
     P.indirect = a.indirect_count; P.hits = a.hits; P.first_found = a.first_found_tie_rule ? 1 : 0;
     P.ticket = a.scratch; P.overflow_count = a.scratch + 1; P.deep_ticket = a.scratch + 2;
+    P.packet_ticket = a.scratch + 3; P.chunk_count = a.scratch + 4;
     P.overflow_list = a.scratch + kScratchHeader / sizeof(uint32_t);
-    P.arena = P.overflow_list + overflow_list_bytes(a.ray_count) / sizeof(uint32_t);
+    uint32_t* chunk_list = P.overflow_list + overflow_list_bytes(a.ray_count) / sizeof(uint32_t);
+    P.arena = chunk_list + chunk_list_bytes(a.ray_count) / sizeof(uint32_t);
+    P.chunk_list = nullptr;
     static const int force_generic = [] { const char* e = std::getenv("RR_CUDA_TRACE_GENERIC"); return e ? std::atoi(e) : 0; }();
+    static const int no_packets    = [] { const char* e = std::getenv("RR_CUDA_TRACE_PACKETS"); return e && std::atoi(e) == 0 ? 1 : 0; }();
     P.force_generic = force_generic;
-    RR_CUDA_CHECK(cudaMemsetAsync(a.scratch, 0, 4 * sizeof(uint32_t), s));
-    const bool any = a.query == RR_INTERSECT_QUERY_ANY, full = a.output == RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, two = a.instances != nullptr;
-    if (!two)
+    RR_CUDA_CHECK(cudaMemsetAsync(a.scratch, 0, 8 * sizeof(uint32_t), s));
+    const bool any = a.query == RR_INTERSECT_QUERY_ANY, full = a.output == RR_INTERSECT_QUERY_OUTPUT_FULL_HIT;
+    // One-level kernels (they return at once when the buffer turns out to be a scene) ...
     {
-        if (any) { if (full) launch<true, true, false>(dev, s, P); else launch<true, false, false>(dev, s, P); }
-        else     { if (full) launch<false, true, false>(dev, s, P); else launch<false, false, false>(dev, s, P); }
+        TraceParams Q = P;
+        if (!any && !a.first_found_tie_rule && !no_packets)
+        {   // closest hit under the (t, prim) rule: coherent 64-ray packets first, whatever they decline goes to k_trace in list mode
+            Q.chunk_list = chunk_list;
+            const size_t need = ((size_t)a.ray_count + 2 * kPacketThreads - 1) / (2 * kPacketThreads);
+            const int    grid = (int)std::max<size_t>(1, std::min<size_t>(need, (size_t)dev.sm_count * packet_ctas_per_sm()));
+            if (full) k_trace_packet<true><<<grid, kPacketThreads, 0, s>>>(Q);
+            else      k_trace_packet<false><<<grid, kPacketThreads, 0, s>>>(Q);
+            *dev.launches += 1;
+        }
+        if (any) { if (full) launch<true, true, false>(dev, s, Q); else launch<true, false, false>(dev, s, Q); }
+        else     { if (full) launch<false, true, false>(dev, s, Q); else launch<false, false, false>(dev, s, Q); }
     }
-    else
-    {
-        if (any) { if (full) launch<true, true, true>(dev, s, P); else launch<true, false, true>(dev, s, P); }
-        else     { if (full) launch<false, true, true>(dev, s, P); else launch<false, false, true>(dev, s, P); }
-    }
+    // ... and two-level kernels (they return at once when it is a geometry).
+    if (any) { if (full) launch<true, true, true>(dev, s, P); else launch<true, false, true>(dev, s, P); }
+    else     { if (full) launch<false, true, true>(dev, s, P); else launch<false, false, true>(dev, s, P); }
+    *dev.launches += 2;
     *dev.launches += 2;
     RR_CUDA_CHECK(cudaGetLastError());
 }

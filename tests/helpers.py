@@ -3,6 +3,8 @@ import numpy as np
 
 from oracle import binding as O
 
+HIT_DTYPE_ = O.HIT_DTYPE
+
 FIELDS_EXACT = ("child0", "child1", "parent", "aabb0_min_or_v0", "aabb0_max_or_v1", "aabb1_min_or_v2", "aabb1_max_or_v3")
 
 
@@ -16,8 +18,12 @@ def assert_nodes_equal(got, want, what="nodes"):
         assert bad.size == 0, f"{what}: field {f} differs at {bad.size} nodes, first {bad[:5]}: {got[f][bad[:3]]} vs {want[f][bad[:3]]}"
 
 
-def assert_hits_equal(got, want, rel_uv=1e-6, what="hits"):
-    """ids bit-exact; uv within 1e-6 relative (BASELINE.json north_star) -- in practice they are bit-exact too."""
+def assert_hits_equal(got, want, rel_uv=1e-6, what="hits", mesh=None, rays=None):
+    """ids bit-exact; uv within 1e-6 relative (BASELINE.json north_star) -- in practice they are bit-exact too.
+    mesh=(positions, indices) and rays: the query was CLOSEST under the default (t, prim) rule, which the packet traversal
+    answers -- rays that differ from the BVH2 walk must then carry the brute-force minimum (assert_closest_hits_equal)."""
+    if mesh is not None:
+        return assert_closest_hits_equal(got, want, mesh, rays, what=what)
     assert got.shape == want.shape
     assert np.array_equal(got["inst_id"], want["inst_id"]), f"{what}: inst_id mismatch at {np.nonzero(got['inst_id'] != want['inst_id'])[0][:8]}"
     ok = want["inst_id"] != O.INVALID
@@ -82,3 +88,38 @@ def assert_matches_reference_tracer(hits, ref, what, max_mask_mismatch=4):
     duv = np.abs(hits["uv"][same].astype(np.float64) - rh["uv"][same].astype(np.float64))
     assert duv.size and np.median(duv) < 1e-5 and duv.max() < 5e-2, f"{what}: uv vs reference (u, v): median {np.median(duv)}, max {duv.max()}"
     return int(np.count_nonzero(differs)), int(np.count_nonzero(one)), int(np.count_nonzero(same))
+
+
+def assert_closest_hits_equal(got, want, mesh, rays, what="closest hits", max_fraction=2e-4):
+    """Closest-hit parity under the default (t, prim) tie rule, for the packet traversal (rr_trace.cu k_trace_packet).
+
+    `want` is the oracle's BVH2 walk (isect.comp's visit order).  The result of a closest-hit query is the (t, prim) minimum over
+    the triangles the ray accepts, which does not depend on the visit order -- except where the slab test, by an ulp, hides a
+    triangle from one walk and not from the other (exact-t ties across a culled subtree, rays grazing a flat box).  Those rays
+    must then carry the order-INDEPENDENT answer, the brute-force (t, prim) minimum over all triangles (same triangle arithmetic),
+    and there may only be a handful of them.  Everything else is compared bit for bit as before.  Returns the number of such rays."""
+    pos, idx = mesh
+    full = got.dtype == HIT_DTYPE_
+    gi = got["inst_id"] if full else got
+    wi = want["inst_id"] if full else want
+    differ = gi != wi
+    if full:
+        differ |= (wi != O.INVALID) & (got["prim_id"] != want["prim_id"])
+    n = int(np.count_nonzero(differ))
+    if n:
+        assert n <= max(2, int(max_fraction * got.shape[0])), f"{what}: {n} of {got.shape[0]} rays differ from the BVH2 walk"
+        bf, _ = O.brute_force(pos, idx, rays[differ])
+        if full:
+            assert np.array_equal(got["inst_id"][differ], bf["inst_id"]) and np.array_equal(got["prim_id"][differ], bf["prim_id"]), \
+                f"{what}: a ray that differs from the BVH2 walk does not carry the brute-force (t, prim) minimum"
+            a, b = got["uv"][differ].astype(np.float64), bf["uv"].astype(np.float64)
+            assert np.all(np.abs(a - b) <= 1e-6 * np.maximum(np.abs(b), 1e-30) + 1e-12), f"{what}: uv of a tie ray"
+        else:
+            assert np.array_equal(got[differ], np.where(bf["inst_id"] != O.INVALID, bf["prim_id"], O.INVALID)), \
+                f"{what}: a ray that differs from the BVH2 walk does not carry the brute-force (t, prim) minimum"
+    same = ~differ
+    if full:
+        assert_hits_equal(got[same], want[same], what=what)
+    else:
+        assert np.array_equal(got[same], want[same]), what
+    return n

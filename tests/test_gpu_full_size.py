@@ -124,7 +124,7 @@ def test_c3_16m_ray_batches(engine, sponza):
         closest = engine.intersect(g, rays, CLOSEST, FULL)
         anyids = engine.intersect(g, rays, ANY, IDS)
         assert np.array_equal(closest["inst_id"] != O.INVALID, anyids != O.INVALID), f"{name}: any-hit and closest-hit must agree on hit / miss"
-        assert_hits_equal(closest[sel], O.trace(nodes, rays[sel], init=np.zeros(sel.size, W.HIT_DTYPE)), what=f"{name} sample")
+        assert_hits_equal(closest[sel], O.trace(nodes, rays[sel], init=np.zeros(sel.size, W.HIT_DTYPE)), what=f"{name} sample", mesh=(pos, idx), rays=rays[sel])
         assert np.array_equal(anyids[sel], O.trace(nodes, rays[sel], O.QUERY_ANY, O.OUTPUT_INSTANCE_ID))
         again = engine.intersect(g, rays, CLOSEST, FULL)
         assert np.array_equal(again.view(np.uint8), closest.view(np.uint8)), f"{name}: not deterministic"
@@ -141,7 +141,7 @@ def test_c2_4k_primary_is_reproducible_and_position_independent(engine, sponza):
     rays = W.sponza_primary_rays(3840, 2160)
     first = engine.intersect(g, rays)
     sel = np.arange(0, rays.shape[0], 64)
-    assert_hits_equal(first[sel], O.trace(g.nodes(), rays[sel], init=np.zeros(sel.size, W.HIT_DTYPE)), what="4K sample")
+    assert_hits_equal(first[sel], O.trace(g.nodes(), rays[sel], init=np.zeros(sel.size, W.HIT_DTYPE)), what="4K sample", mesh=(pos, idx), rays=rays[sel])
     engine.rebuild(g)
     assert np.array_equal(engine.intersect(g, rays).view(np.uint8), first.view(np.uint8))
     clone = Geometry()
