@@ -8,7 +8,10 @@ closest-hit rays, FULL_HIT output.  A "step" is one rrCmd
 8 294 400-ray batch.  `value` is timed with CUDA events around K steps with rays/BVH resident in HBM;
 `e2e` is the same step through the rr* C ABI with HOST (pinned) ray and hit buffers, copies inside the
 timed region.  N>1: one process per GPU (torchrun), BLAS built on rank 0 and broadcast over NCCL (it holds
-indices, not pointers), every rank traces its own full batch (weak scaling, no data-path collective).
+indices, not pointers); the global batch is N such frames sharded contiguously, rank r traces frame r and its
+traversal kernels store the hits straight into rank 0's buffer over NVLink (CUDA IPC peer mapping), inside the timed
+region (weak scaling in the batch size, with the gather of every hit to one rank included).  `c3_strong` in the same
+line is BASELINE config C3: ONE 16 Mi-ray batch (diffuse CLOSEST, shadow ANY) sharded over the ranks, strong scaling.
 
 --impl reference times the reference's own CPU tracer (bvh_analyzer, compiled from /root/reference into
 oracle/_ref by oracle/Makefile; falls back to the oracle port if that binary is absent) on the box's host cores.
@@ -28,8 +31,7 @@ sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT = 3840, 2160
 BYTES_PER_RAY = 48           # 32 B ray read + 16 B RRHit write: the compulsory HBM traffic
-TRACE_DRAM_BYTES_PER_LAUNCH = 357_213_952   # dram__bytes_read+write of one C2 launch, ncu --set full (profiles/round1_summary.md)
-LANE_VISITS_PER_RAY = 66.6   # warp-iterations x 32 / rays of the C2 batch on the quality BVH (ncu instruction counts, same file)
+PCIE_GEN5_X16_GBS = 63.0     # per direction
 BUILD_BYTES_PER_TRI = 348    # 48 aabb + 48 morton + 4 code + 60 sort + 12 emit reads + 48 gather + 128 nodes
 
 
@@ -147,10 +149,25 @@ def dist_setup(n_gpus):
     return rank, world, local
 
 
+def workload_config(n_tris, n_rays, bvh, world):
+    """`config` of the JSON line: the same dict in both arms (the reference arm always reports the N=1 form)."""
+    return {"workload": f"C2: Sponza {n_tris} tris, HLBVH build + {WIDTH}x{HEIGHT} coherent primary closest-hit rays, FULL_HIT",
+            "rays_per_step_per_gpu": n_rays, "bvh": f"{bvh} build",
+            "parallelism": "1 GPU" if world == 1 else f"global batch of {world} frames sharded over {world} ranks (one frame each), BLAS broadcast over NCCL, "
+                           "hits of all ranks gathered into rank 0's buffer by peer stores from the traversal kernels, inside the timed region",
+            "l2": "ray+hit buffers per step (398 MB) exceed the 126 MB L2; the 33.6 MB BVH is meant to stay L2 resident"}
+
+
+def load_ncu_summary():
+    """profiles/round2_ncu_trace.json, written by tools/ncu_extract.py from the committed ncu capture of the dominant kernel."""
+    p = os.path.join(ROOT, "profiles", "round2_ncu_trace.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from radeonrays_sdk_b200 import api, workloads as W
+    from radeonrays_sdk_b200 import api, sharding, workloads as W
     from radeonrays_sdk_b200.host import Engine
 
     rank, world, local = dist_setup(args.gpus)
@@ -158,6 +175,8 @@ def run_ours(args):
     ctx, dev = eng.ctx, eng.device
     pos, idx, _ = W.load_mesh("sponza")
     n_tris = idx.shape[0]
+    CLOSEST, ANY = api.RR_INTERSECT_QUERY_CLOSEST, api.RR_INTERSECT_QUERY_ANY
+    FULL, IDS = api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, api.RR_INTERSECT_QUERY_OUTPUT_INSTANCE_ID
 
     def barrier():
         if world > 1:
@@ -179,21 +198,23 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- build (timed separately: HLBVH build Mtris/s, fast and quality) --------------------------------
-    g_fast = eng.build_geometry(pos, idx, build_flags=api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD)
-    g_qual = eng.build_geometry(pos, idx, build_flags=0)
+    streams = []
 
     def resubmitter(record):
         cs = ctx.allocate_command_stream()
         record(cs)
+        streams.append(cs)
 
         def go():
             ctx.release_event(ctx.submit(cs))
-        return go, cs
+        return go
 
-    build_fast, cs1 = resubmitter(lambda s: ctx.cmd_build_geometry(api.RR_BUILD_OPERATION_BUILD, g_fast.input, g_fast.options, g_fast.p_temp, g_fast.p_nodes, s))
-    build_qual, cs2 = resubmitter(lambda s: ctx.cmd_build_geometry(api.RR_BUILD_OPERATION_BUILD, g_qual.input, g_qual.options, g_qual.p_temp, g_qual.p_nodes, s))
-    refit, cs3 = resubmitter(lambda s: ctx.cmd_build_geometry(api.RR_BUILD_OPERATION_UPDATE, g_fast.input, g_fast.options, g_fast.p_temp, g_fast.p_nodes, s))
+    # ---- build (timed separately: HLBVH build Mtris/s, fast and quality) --------------------------------
+    g_fast = eng.build_geometry(pos, idx, build_flags=api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD)
+    g_qual = eng.build_geometry(pos, idx, build_flags=0)
+    build_fast = resubmitter(lambda s: ctx.cmd_build_geometry(api.RR_BUILD_OPERATION_BUILD, g_fast.input, g_fast.options, g_fast.p_temp, g_fast.p_nodes, s))
+    build_qual = resubmitter(lambda s: ctx.cmd_build_geometry(api.RR_BUILD_OPERATION_BUILD, g_qual.input, g_qual.options, g_qual.p_temp, g_qual.p_nodes, s))
+    refit = resubmitter(lambda s: ctx.cmd_build_geometry(api.RR_BUILD_OPERATION_UPDATE, g_fast.input, g_fast.options, g_fast.p_temp, g_fast.p_nodes, s))
     l0 = ctx.launch_count()
     build_fast()
     launches_per_fast_build = ctx.launch_count() - l0
@@ -207,33 +228,79 @@ def run_ours(args):
     if world > 1:
         dist.broadcast(geom.d_nodes, src=0)
 
-    # ---- trace: device-resident ---------------------------------------------------------------------------
-    rays = W.sponza_primary_rays(WIDTH, HEIGHT)
+    # ---- trace: rays resident in HBM ------------------------------------------------------------------------
+    # Global batch = `world` camera frames of 3840x2160 primary rays (frame r: the canonical camera raised by r/2 units), sharded
+    # contiguously: rank r traces frame r.  N=1: hits go to a local buffer.  N>1: the hit buffer of the WHOLE batch lives on rank 0
+    # and is mapped into every rank (sharding.PeerHitBuffer); each rank's traversal kernels store their hits straight into it
+    # over NVLink while they trace -- the gather is inside the timed region, fused with the compute.
+    def frame_rays(r):
+        rays = W.sponza_primary_rays(WIDTH, HEIGHT)
+        rays["origin"][:, 1] += np.float32(0.5 * r)
+        return rays
+
+    rays = frame_rays(rank)
     n_rays = rays.shape[0]
     rb = eng.make_ray_buffers(n_rays)
     h_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).pin_memory()
     h_hits = torch.empty(16 * n_rays, dtype=torch.uint8).pin_memory()
     rb.d_rays[: 32 * n_rays].copy_(h_rays)
-    trace, cs4 = resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, api.RR_INTERSECT_QUERY_CLOSEST, rb.p_rays, n_rays, None,
-                                                         api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, rb.p_hits, rb.p_scratch, s))
+    peer = None
+    p_hits = rb.p_hits
+    if world > 1:
+        peer = sharding.PeerHitBuffer(ctx, world * 16 * n_rays, root=0)
+        p_hits = peer.ptr(rank * 16 * n_rays)
+    trace = resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, CLOSEST, rb.p_rays, n_rays, None, FULL, p_hits, rb.p_scratch, s))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count()
     ms_total = timed(trace, args.steps, args.warmup)
-    launches = (ctx.launch_count() - l0) * args.steps // (args.steps + args.warmup)   # k_trace + k_trace_deep per step
+    launches = (ctx.launch_count() - l0) // (args.steps + args.warmup)   # kernels per step (packet + per-ray + deep, one- and two-level)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     mrays = world * n_rays / (ms_step * 1e-3) / 1e6
 
-    # the other trace flavours of the metric (any-hit; fast-build BVH), device resident, same batch
-    other = g_fast if geom is g_qual else g_qual
-    trace_other, cs5 = resubmitter(lambda s: ctx.cmd_intersect(other.p_nodes, api.RR_INTERSECT_QUERY_CLOSEST, rb.p_rays, n_rays, None,
-                                                               api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, rb.p_hits, rb.p_scratch, s))
-    ms_other = timed(trace_other, args.steps, 1) / args.steps
-    trace_any, cs6 = resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, api.RR_INTERSECT_QUERY_ANY, rb.p_rays, n_rays, None,
-                                                             api.RR_INTERSECT_QUERY_OUTPUT_INSTANCE_ID, rb.p_hits, rb.p_scratch, s))
-    ms_any = timed(trace_any, args.steps, 1) / args.steps
+    multi = None
+    if world > 1:
+        # (a) what rank 0 now holds must be what it gets by tracing every frame itself
+        ok = True
+        if rank == 0:
+            got = peer.read(W.HIT_DTYPE).reshape(world, n_rays)
+            for r in range(world):
+                want = eng.intersect(geom, frame_rays(r))
+                ok = ok and bool(np.array_equal(got[r].view(np.uint8), want.view(np.uint8)))
+        # (b) comparison arm: trace into a local buffer, then one NCCL gather to rank 0
+        local_trace = resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, CLOSEST, rb.p_rays, n_rays, None, FULL, rb.p_hits, rb.p_scratch, s))
+        dst = [torch.empty(16 * n_rays, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        src = rb.d_hits[: 16 * n_rays]
+
+        def nccl_step():
+            local_trace()
+            torch.cuda.current_stream(dev).wait_stream(eng.torch_stream)
+            dist.gather(src, dst, dst=0)
+
+        def nccl_only():
+            dist.gather(src, dst, dst=0)
+        ms_nccl = timed(nccl_step, max(3, args.steps // 4), 2) / max(3, args.steps // 4)
+        ms_gather = timed(nccl_only, max(3, args.steps // 4), 2) / max(3, args.steps // 4)
+        ms_local = timed(local_trace, max(3, args.steps // 4), 2) / max(3, args.steps // 4)
+        multi = {"hits_gathered_on_rank0_inside_timed_region": True, "gather": "traversal kernels store hits into rank 0's buffer through CUDA IPC / NVLink peer mappings",
+                 "rank0_buffer_equals_local_trace_of_every_frame": ok, "nvlink_bytes_per_step": (world - 1) * 16 * n_rays,
+                 "nvlink_gbs_into_rank0": round((world - 1) * 16 * n_rays / (ms_step * 1e-3) / 1e9, 1),
+                 "local_trace_only_ms": round(ms_local, 4), "nccl_gather_only_ms": round(ms_gather, 4),
+                 "trace_then_nccl_gather_ms": round(ms_nccl, 4), "fused_ms": round(ms_step, 4)}
+
+    # the other trace flavours of the metric (any-hit; the other BVH; the per-ray kernel), device resident, same batch (N=1 only)
+    variants = None
+    if world == 1:
+        other = g_fast if geom is g_qual else g_qual
+        ms_other = timed(resubmitter(lambda s: ctx.cmd_intersect(other.p_nodes, CLOSEST, rb.p_rays, n_rays, None, FULL, rb.p_hits, rb.p_scratch, s)), args.steps, 1) / args.steps
+        ms_any = timed(resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, ANY, rb.p_rays, n_rays, None, IDS, rb.p_hits, rb.p_scratch, s)), args.steps, 1) / args.steps
+        ctx.set_option(api.RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, 1)      # the reference's tie rule: per-ray kernel (k_trace), no packets
+        ms_ff = timed(resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, CLOSEST, rb.p_rays, n_rays, None, FULL, rb.p_hits, rb.p_scratch, s)), args.steps, 1) / args.steps
+        ctx.set_option(api.RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, 0)
+        variants = {"closest_full_hit_other_bvh_mrays": round(n_rays / ms_other / 1e3, 1), "any_hit_ids_mrays": round(n_rays / ms_any / 1e3, 1),
+                    "closest_first_found_rule_per_ray_kernel_mrays": round(n_rays / ms_ff / 1e3, 1)}
 
     # ---- trace: end to end through the C ABI with host buffers ------------------------------------------------
     from radeonrays_sdk_b200.host import HostTracePipeline
@@ -247,6 +314,17 @@ def run_ours(args):
     e2e_mrays = world * n_rays / (ms_e2e * 1e-3) / 1e6
     hits = h_hits.numpy().view(W.HIT_DTYPE)
     hit_fraction = float((hits["inst_id"] != W.INVALID).mean())
+    pcie_gbs = 48 * n_rays / (ms_e2e * 1e-3) / 1e9
+
+    # ---- config C3: one 16 Mi-ray batch (diffuse CLOSEST / FULL_HIT and shadow ANY / ids) sharded over the ranks, strong scaling ----
+    c3 = None
+    if not args.no_c3:
+        c3 = c3_strong(eng, geom, pos, idx, rank, world, timed, resubmitter)
+
+    # ---- config C4: 1 000 instanced Sponza BLASes under a TLAS (N=1) ------------------------------------------------
+    c4 = None
+    if world == 1 and not args.no_c4:
+        c4 = scene_c4(eng, geom, timed, resubmitter)
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
@@ -259,31 +337,28 @@ def run_ours(args):
         c5 = build_c5(eng)
 
     peak, peak_src = measured_peak_gbs()
-    l1_peak_visits = 2.0 * eng.sm_count * (clocks["sm_max_mhz"] if clocks and clocks.get("sm_max_mhz") else 1965.0) * 1e6
     achieved = BYTES_PER_RAY * n_rays / (ms_step * 1e-3) / 1e9
     build_gbs = BUILD_BYTES_PER_TRI * n_tris / (ms_fast * 1e-3) / 1e9
+    ncu = load_ncu_summary()
+    same_kernel_config = ncu is not None and (n_rays, args.bvh) == (WIDTH * HEIGHT, "quality")
     out = {
         "metric": "Mrays/s closest-hit (Sponza)", "value": round(mrays, 2), "unit": "Mrays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic rays on the Sponza fixture (tests/golden/sponza.npz)",
-        "config": {"workload": f"C2: Sponza {n_tris} tris, HLBVH build + {WIDTH}x{HEIGHT} coherent primary closest-hit rays, FULL_HIT",
-                   "rays_per_step_per_gpu": n_rays, "bvh": f"{args.bvh} build", "parallelism": f"ray shards x{world}, BLAS broadcast",
-                   "l2": "ray+hit buffers per step (398 MB) exceed the 126 MB L2; the 33.6 MB BVH is meant to stay L2 resident"},
+        "config": workload_config(n_tris, n_rays, args.bvh, world),
         "e2e": {"value": round(e2e_mrays, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n_rays * world, "d2h_bytes_per_step": 16 * n_rays * world,
                 "ms_per_step": round(ms_e2e, 4), "pipeline": f"{args.e2e_chunks} slices, H2D / rrCmdIntersect / D2H on three streams",
-                "cpus_bound_to_gpu": BOUND_CPUS},
+                "cpus_bound_to_gpu": BOUND_CPUS, "bound": "pcie", "pcie_gbs_per_gpu_both_directions": round(pcie_gbs, 1),
+                "pcie_wire_fraction": round(pcie_gbs / 2 / PCIE_GEN5_X16_GBS, 3),
+                "note": "48 B per ray cross PCIe (32 in, 16 out); wire fraction = per-direction average against Gen5 x16 (63 GB/s)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": TRACE_DRAM_BYTES_PER_LAUNCH if (n_rays, args.bvh) == (WIDTH * HEIGHT, "quality") else None,
-                     "peak_source": peak_src, "kernel": "k_trace<closest,full_hit,one_level>",
+                     "traffic": ncu["dram_bytes"] if same_kernel_config else None,
+                     "peak_source": peak_src, "kernel": "k_trace_packet<full_hit> (+ k_trace for declined chunks)",
                      "algorithmic_bytes_per_launch": BYTES_PER_RAY * n_rays,
-                     "note": "48 B/ray compulsory (32 B ray + 16 B hit), BVH L2-resident: HBM is not the bound",
-                     # the binding unit: every lane receives 64 B per visited node through the SM's
-                     # 128 B/clk L1 data pipe => 2 node visits/clk/SM
-                     "l1_data_pipe": {"lane_visits_per_ray": LANE_VISITS_PER_RAY, "peak_visits_per_s": round(l1_peak_visits, 1),
-                                      "achieved_visits_per_s": round(LANE_VISITS_PER_RAY * n_rays / (ms_step * 1e-3), 1),
-                                      "frac": round(LANE_VISITS_PER_RAY * n_rays / (ms_step * 1e-3) / l1_peak_visits, 4),
-                                      "ncu_l1tex_data_pipe_pct": 91.2, "source": "profiles/round1_summary.md section 2"}},
+                     "note": "48 B/ray compulsory (32 B ray + 16 B hit), BVH L2-resident: HBM is not the bound; the kernel is bound by the SM's "
+                             "ALU pipe / issue slots (profiles/round2_summary.md)",
+                     "ncu": ncu if same_kernel_config else None},
         "cpu_baseline": cpu,
         "clocks": clocks,
         "build": {"fast_ms": round(ms_fast, 4), "fast_mtris_per_s": round(n_tris / ms_fast / 1e3, 1), "quality_ms": round(ms_qual, 4),
@@ -291,17 +366,97 @@ def run_ours(args):
                   "refit_mtris_per_s": round(n_tris / ms_refit / 1e3, 1), "launches_per_fast_build": int(launches_per_fast_build),
                   "fast_build_hbm_gbs": round(build_gbs, 1), "fast_build_roofline_frac": round(build_gbs / peak, 4)},
         "build_c5": c5,
-        "trace_variants": {"closest_full_hit_other_bvh_mrays": round(n_rays / ms_other / 1e3, 1),
-                           "any_hit_ids_mrays": round(n_rays / ms_any / 1e3, 1), "hit_fraction": round(hit_fraction, 4)},
+        "c3_strong": c3,
+        "c4_two_level": c4,
+        "multi_gpu": multi,
+        "trace_variants": dict(variants or {}, hit_fraction=round(hit_fraction, 4)),
     }
     if rank == 0:
         print(json.dumps(out), flush=True)
     pipe.close()
-    for cs in (cs1, cs2, cs3, cs4, cs5, cs6):
+    if peer is not None:
+        barrier()
+        peer.close()
+    for cs in streams:
         ctx.release_command_stream(cs)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def c3_strong(eng, geom, pos, idx, rank, world, timed, resubmitter, count=1 << 24, steps=5):
+    """BASELINE config C3: ONE batch of 16 Mi rays (shadow ANY / ids, diffuse-bounce CLOSEST / FULL_HIT) sharded contiguously over
+    the ranks (sharding.shard_range), every rank's hits landing in rank 0's buffer by peer stores from the traversal kernels inside
+    the timed region.  Strong scaling: total work is fixed, the time at N ranks is what a client on rank 0 waits for all hits."""
+    import torch
+    import torch.distributed as dist
+    from radeonrays_sdk_b200 import api, sharding, workloads as W
+    ctx, dev = eng.ctx, eng.device
+    out = {"rays_per_batch": count, "ranks": world}
+    d_rays = {}
+    for name in ("diffuse", "shadow"):
+        t = torch.empty(32 * count, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            prim = W.sponza_primary_rays(1024, 1024)
+            hits = eng.intersect(geom, prim)
+            r = (W.diffuse_rays if name == "diffuse" else W.shadow_rays)(pos, idx, prim, hits, count=count)
+            t.copy_(torch.from_numpy(r.view(np.uint8).reshape(-1)))
+        if world > 1:
+            dist.broadcast(t, src=0)
+        d_rays[name] = t
+    b, e = sharding.shard_range(count, rank, world)
+    scratch = torch.empty(max(ctx.trace_requirements(e - b), 256), dtype=torch.uint8, device=dev)
+    p_scratch = ctx.tensor_ptr(scratch)
+    for name, query, output, item in (("diffuse", api.RR_INTERSECT_QUERY_CLOSEST, api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, 16),
+                                      ("shadow", api.RR_INTERSECT_QUERY_ANY, api.RR_INTERSECT_QUERY_OUTPUT_INSTANCE_ID, 4)):
+        p_rays = ctx.tensor_ptr(d_rays[name], 32 * b)
+        peer, local = None, None
+        if world > 1:
+            peer = sharding.PeerHitBuffer(ctx, item * count, root=0)
+            p_hits = peer.ptr(item * b)
+        else:
+            local = torch.empty(item * count, dtype=torch.uint8, device=dev)
+            p_hits = ctx.tensor_ptr(local)
+        go = resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, query, p_rays, e - b, None, output, p_hits, p_scratch, s))
+        ms = timed(go, steps, 2) / steps
+        out[name + "_ms"] = round(ms, 4)
+        out[name + "_mrays_per_s"] = round(count / ms / 1e3, 1)
+        if world > 1:
+            out[name + "_nvlink_bytes_into_rank0"] = item * (count - (sharding.shard_range(count, 0, world)[1]))
+            if dist.get_rank() == 0:
+                got = peer.read(np.uint8)
+                sel = np.arange(0, count, 4099)
+                full = got.view(W.HIT_DTYPE)["inst_id"] if item == 16 else got.view(np.uint32)
+                out[name + "_hit_fraction"] = round(float((full[sel] != W.INVALID).mean()), 4)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+            peer.close()
+    return out
+
+
+def scene_c4(eng, geom, timed, resubmitter, steps=5):
+    """BASELINE config C4: 1 000 rotated instances of the Sponza BLAS under one TLAS, rrCmdBuildScene + 3840x2160 primary rays
+    from outside the grid, two-level rrCmdIntersect (closest, FULL_HIT)."""
+    import torch
+    from radeonrays_sdk_b200 import api, workloads as W
+    ctx, dev = eng.ctx, eng.device
+    xf = W.grid_instances(10, 250.0, 7.0)
+    sc = eng.build_scene([geom], [0] * xf.shape[0], xf)
+    # scene builds stage the host instance array: submitted directly, not replayed as a graph
+    cs = ctx.allocate_command_stream()
+    ctx.cmd_build_scene(sc.input, None, sc.p_temp, sc.p_nodes, cs)
+    ms_scene = timed(lambda: ctx.release_event(ctx.submit(cs)), steps, 1) / steps
+    ctx.release_command_stream(cs)
+    rays = W.grid_camera_rays(WIDTH, HEIGHT)
+    n = rays.shape[0]
+    rb = eng.make_ray_buffers(n)
+    rb.d_rays[: 32 * n].copy_(torch.from_numpy(rays.view(np.uint8).reshape(-1)))
+    go = resubmitter(lambda s: ctx.cmd_intersect(sc.p_nodes, api.RR_INTERSECT_QUERY_CLOSEST, rb.p_rays, n, None, api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT,
+                                                 rb.p_hits, rb.p_scratch, s))
+    ms = timed(go, steps, 1) / steps
+    hits = rb.d_hits[: 16 * n].cpu().numpy().view(W.HIT_DTYPE)
+    return {"workload": f"C4: {xf.shape[0]} instances of the Sponza BLAS, rotated 10x10x10 grid, {WIDTH}x{HEIGHT} primary rays", "scene_build_ms": round(ms_scene, 4),
+            "trace_ms": round(ms, 4), "trace_mrays_per_s": round(n / ms / 1e3, 1), "hit_fraction": round(float((hits["inst_id"] != W.INVALID).mean()), 4)}
 
 
 def build_c5(eng, nx=5000, nz=5000, reps=5):
@@ -363,26 +518,49 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(nodes, rays, budget_rays=None):
-    """Reference CPU tracer (oracle/_ref/bvh_analyzer_trace) or the oracle port on a bounded sample of the batch."""
+def reference_rays():
+    """The C2 batch as the reference's CPU tracer must be given it: every direction multiplied by a power of two so that all
+    |components| >= 1 (workloads.pow2_scaled_rays: bit-identical hits; bvh_analyzer's `abs` is the integer overload under g++ and
+    mis-traverses any ray with a |component| < 1, which would make it look several times faster than it is)."""
+    from radeonrays_sdk_b200 import workloads as W
+    rays, _ = W.pow2_scaled_rays(W.sponza_primary_rays(WIDTH, HEIGHT), keep_all=True)
+    return rays
+
+
+def cpu_baseline(nodes, rays):
+    """Reference CPU tracer (oracle/_ref/bvh_analyzer_trace: the `#pragma omp parallel for` loop over BvhIntersect<2> of
+    bvh_analyzer/bvh.h:87-93 with its stock scheduling) on the FULL C2 batch, or the oracle port if that binary is absent; plus one
+    run of the unmodified stock binary on the 7-line config (a 960x540 sub-sample: it serialises every ray on an omp critical)."""
     from oracle import binding as O
-    sample = rays.reshape(HEIGHT, WIDTH)[::4, ::2].reshape(-1)   # 1 036 800 rays, every 4th row / 2nd column
-    desc = f"{sample.shape[0]} rays = rows[::4], cols[::2] of the {WIDTH}x{HEIGHT} batch"
-    res = O.ref_bvh_analyzer_trace(nodes, sample, repeats=3, threads=host_threads())
+    from radeonrays_sdk_b200 import workloads as W
+    full = reference_rays()
+    desc = f"all {full.shape[0]} rays of the {WIDTH}x{HEIGHT} batch (directions scaled by powers of two, same hits)"
+    res = O.ref_bvh_analyzer_trace(nodes, full, repeats=2, threads=host_threads(), stock_schedule=True)
     if res is not None and res.get("is_valid"):
-        return {"value": round(res["mrays_per_s"], 3), "unit": "Mrays/s", "cores": res["threads"], "kind": "reference",
-                "sample": desc + "; bvh_analyzer BvhIntersect<2> loop only (bvh.h:87-93), 3 repeats, mean",
-                "bvh_is_valid": True, "reference_sah": res["sah"]}
+        out = {"value": round(res["mrays_per_s"], 3), "unit": "Mrays/s", "cores": res["threads"], "kind": "reference",
+               "sample": desc + "; bvh_analyzer BvhIntersect<2> loop only (bvh.h:87-93), stock `omp parallel for`, 2 repeats, mean",
+               "bvh_is_valid": True, "reference_sah": res["sah"], "hit_fraction": round(res["hit_count"] / full.shape[0], 4),
+               "avg_node_tests": res["avg_node_tests"], "avg_triangle_tests": res["avg_tri_tests"]}
+        sub, _ = W.pow2_scaled_rays(W.sponza_primary_rays(960, 540), keep_all=True)
+        stock = O.ref_bvh_analyzer_stock(nodes, sub, 960, 540, threads=host_threads())
+        if stock is not None:
+            out["stock_binary"] = {"config": "7-line config (bvh_analyzer/config.h:46-63), 960x540 rays", "returncode": stock["returncode"],
+                                   "is_valid": stock.get("is_valid"), "sah": stock.get("sah"), "avg_primary_node_tests": stock.get("avg_primary_node_tests"),
+                                   "avg_primary_triangle_tests": stock.get("avg_primary_triangle_tests"), "wall_s": round(stock["wall_s"], 2),
+                                   "mrays_per_s_end_to_end": round(sub.shape[0] / stock["wall_s"] / 1e6, 3)}
+        return out
+    sample = full.reshape(HEIGHT, WIDTH)[::4, ::2].reshape(-1)
     t0 = time.time()
     O.trace(nodes, sample)
     dt = time.time() - t0
     return {"value": round(sample.shape[0] / dt / 1e6, 3), "unit": "Mrays/s", "cores": O.num_threads(), "kind": "port",
-            "sample": desc + "; oracle/rr_oracle.c rro_trace (OpenMP)"}
+            "sample": f"{sample.shape[0]} rays = rows[::4], cols[::2] of the batch; oracle/rr_oracle.c rro_trace (OpenMP)"}
 
 
 def run_reference(args):
-    """The reference arm: RadeonRays' own CPU path (bvh_analyzer) on this box's host cores, same metric/config.
-    The BVH it traces is built by the CPU oracle (the reference has no CPU builder)."""
+    """The reference arm: RadeonRays' own CPU path (bvh_analyzer) on this box's host cores, same metric / config: every step
+    traces the FULL 3840x2160 batch with the stock `#pragma omp parallel for` (same_config).  The BVH it traces is built by the
+    CPU oracle (the reference has no CPU builder)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
@@ -391,32 +569,38 @@ def run_reference(args):
     from radeonrays_sdk_b200 import workloads as W
     pos, idx, _ = W.load_mesh("sponza")
     nodes, _, _ = O.build_blas(pos, idx, restructure=(args.bvh == "quality"))
-    rays = W.sponza_primary_rays(WIDTH, HEIGHT)
-    sample = rays.reshape(HEIGHT, WIDTH)[::4, ::2].reshape(-1)
+    rays = reference_rays()
     exe = os.path.join(ROOT, "oracle", "_ref", "bvh_analyzer_trace")
     kind = "reference" if os.path.exists(exe) else "port"
-    times = []
-    cores = O.num_threads()
-    for step in range(args.warmup + args.steps):
-        if kind == "reference":
-            res = O.ref_bvh_analyzer_trace(nodes, sample, repeats=1, threads=host_threads())
-            dt, cores = res["mean_s"], res["threads"]
-        else:
+    cores, unscaled = O.num_threads(), None
+    if kind == "reference":
+        if args.warmup:
+            O.ref_bvh_analyzer_trace(nodes, rays, repeats=args.warmup, threads=host_threads(), stock_schedule=True)
+        res = O.ref_bvh_analyzer_trace(nodes, rays, repeats=args.steps, threads=host_threads(), stock_schedule=True)
+        ms, cores = 1e3 * res["mean_s"], res["threads"]
+        # for the record: the same binary on the batch as generated (|direction components| < 1): most rays are mis-traversed and miss
+        raw = O.ref_bvh_analyzer_trace(nodes, W.sponza_primary_rays(WIDTH, HEIGHT), repeats=1, threads=host_threads(), stock_schedule=True)
+        unscaled = {"mrays_per_s": round(raw["mrays_per_s"], 3), "hit_fraction": round(raw["hit_count"] / rays.shape[0], 4),
+                    "hit_fraction_scaled": round(res["hit_count"] / rays.shape[0], 4)}
+        desc = f"all {rays.shape[0]} rays per step, bvh_analyzer BvhIntersect<2> loop (bvh.h:87-93), stock omp scheduling; directions scaled by powers of two"
+    else:
+        rays = rays.reshape(HEIGHT, WIDTH)[::4, ::2].reshape(-1)
+        times = []
+        for step in range(args.warmup + args.steps):
             t0 = time.time()
-            O.trace(nodes, sample)
-            dt = time.time() - t0
-        if step >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * float(np.mean(times))
-    v = sample.shape[0] / (ms * 1e-3) / 1e6
-    desc = f"{sample.shape[0]} rays per step = rows[::4], cols[::2] of the {WIDTH}x{HEIGHT} batch"
+            O.trace(nodes, rays)
+            if step >= args.warmup:
+                times.append(time.time() - t0)
+        ms = 1e3 * float(np.mean(times))
+        desc = f"{rays.shape[0]} rays per step = rows[::4], cols[::2] of the batch; oracle port (oracle/_ref absent)"
+    v = rays.shape[0] / (ms * 1e-3) / 1e6
     print(json.dumps({
         "impl": "reference", "metric": "Mrays/s closest-hit (Sponza)", "value": round(v, 3), "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic rays on the Sponza fixture",
-        "config": {"workload": f"C2: Sponza {idx.shape[0]} tris, {WIDTH}x{HEIGHT} coherent primary closest-hit rays (bounded sample per step)",
-                   "bvh": f"{args.bvh} build (CPU oracle)"},
-        "cpu_baseline": {"value": round(v, 3), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": desc},
+        "config": workload_config(idx.shape[0], rays.shape[0], args.bvh, 1),
+        "cpu_baseline": {"value": round(v, 3), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": desc,
+                         "bvh_built_by": "CPU oracle (the reference has no CPU builder)", "unscaled_rays": unscaled},
         "e2e": {"value": round(v, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -430,6 +614,8 @@ def main():
     ap.add_argument("--bvh", default="quality", choices=["quality", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the 50 M-triangle build / refit leg (N=1 only; ~2 s, 9 GB)")
+    ap.add_argument("--no-c3", action="store_true", help="skip the 16 Mi-ray shadow / diffuse strong-scaling leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 1 000-instance two-level leg (N=1 only)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="slices of the host batch pipelined through H2D / trace / D2H")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -63,6 +63,16 @@ RR_API RRError rrCudaSetOption(RRContext context, RRCudaOption option, int value
 RR_API RRError rrCudaCmdRebindSceneGeometry(RRContext context, RRDevicePtr scene_buffer, void* old_geometry_address,
                                             RRDevicePtr new_geometry, RRCommandStream command_stream);
 
+/* Multi-GPU plumbing, one process per GPU (no reference counterpart, RadeonRays drives one device).
+ * rrCudaExportDeviceMemory writes an opaque RR_CUDA_IPC_HANDLE_SIZE-byte handle for the allocation behind `device_ptr` and the
+ * byte offset of `device_ptr` inside it; ship both to another process (any transport), whose rrCudaImportDeviceMemory maps the
+ * allocation into ITS address space over NVLink / PCIe peer access and returns an RRDevicePtr at the same offset.  That pointer can
+ * be passed as the `hits` argument of rrCmdIntersect: the traversal kernels then store every hit straight into the remote buffer
+ * while they trace (a fused compute + gather; no staging copy, no separate collective).  Release it with rrReleaseDevicePtr. */
+#define RR_CUDA_IPC_HANDLE_SIZE 64
+RR_API RRError rrCudaExportDeviceMemory(RRContext context, RRDevicePtr device_ptr, void* handle_out, size_t* offset_out);
+RR_API RRError rrCudaImportDeviceMemory(RRContext context, const void* handle, size_t offset, RRDevicePtr* device_ptr);
+
 /* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches evidence). */
 RR_API RRError rrCudaGetLaunchCount(RRContext context, uint64_t* launches);
 

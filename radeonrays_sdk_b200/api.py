@@ -100,6 +100,8 @@ SIGNATURES = {
     "rrCudaSetOption": [_vp, C.c_int, C.c_int],
     "rrCudaGetLaunchCount": [_vp, C.POINTER(C.c_uint64)],
     "rrCudaCmdRebindSceneGeometry": [_vp, _vp, _vp, _vp, _vp],
+    "rrCudaExportDeviceMemory": [_vp, _vp, _vp, C.POINTER(C.c_size_t)],
+    "rrCudaImportDeviceMemory": [_vp, _vp, C.c_size_t, C.POINTER(_vp)],
     # radeonrays_cuda_debug.h
     "rrCudaDebugGetBuildScratchLayout": [_vp, C.c_uint32, C.POINTER(RRCudaBuildScratchLayout)],
     "rrCudaDebugSortPairs": [_vp, _vp, _vp, _vp, _vp, C.c_uint32],
@@ -282,6 +284,20 @@ class Context:
     def cmd_rebind_scene_geometry(self, scene_ptr, old_address, new_geometry_ptr, stream):
         check(self.lib.rrCudaCmdRebindSceneGeometry(self.handle, scene_ptr, _vp(int(old_address)), new_geometry_ptr, stream),
               "rrCudaCmdRebindSceneGeometry")
+
+    def export_memory(self, ptr):
+        """-> (64-byte handle, offset) naming the allocation behind `ptr` for another process (rrCudaExportDeviceMemory)."""
+        h = (C.c_ubyte * 64)()
+        off = C.c_size_t()
+        check(self.lib.rrCudaExportDeviceMemory(self.handle, ptr, C.cast(h, _vp), C.byref(off)), "rrCudaExportDeviceMemory")
+        return bytes(h), off.value
+
+    def import_memory(self, handle, offset=0):
+        """RRDevicePtr onto another process's allocation (rrCudaImportDeviceMemory); release with release_ptr."""
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = _vp()
+        check(self.lib.rrCudaImportDeviceMemory(self.handle, C.cast(buf, _vp), offset, C.byref(p)), "rrCudaImportDeviceMemory")
+        return p
 
     # ---- options / debug -------------------------------------------------------------------------------------
     def set_option(self, option, value):

@@ -61,6 +61,7 @@ struct DevicePtr
     size_t offset      = 0;
     size_t size        = 0;        // 0 = unknown (client memory)
     bool   owned       = false;    // allocated by rrAllocateDeviceBuffer
+    bool   imported    = false;    // mapped from another process by rrCudaImportDeviceMemory
     void*  host_shadow = nullptr;  // pinned mapping while mapped
     char*  ptr() const { return base + offset; }
     size_t bytes_available() const { return size ? size - offset : (size_t)-1; }
@@ -68,6 +69,7 @@ struct DevicePtr
     {
         if (host_shadow) cudaFreeHost(host_shadow);
         if (owned && base) cudaFree(base);
+        if (imported && base) cudaIpcCloseMemHandle(base);
     }
 };
 
@@ -613,6 +615,55 @@ RRError rrCudaCmdRebindSceneGeometry(RRContext context, RRDevicePtr scene_buffer
         const void*      neu   = D(new_geometry)->ptr();
         if (!aligned_to(scene, 64) || !aligned_to(neu, 64)) return RR_ERROR_INVALID_PARAMETER;
         S(command_stream)->commands.push_back([=](cudaStream_t s) { rebind_scene(dev, s, scene, old_geometry_address, neu); });
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == RR_CUDA_IPC_HANDLE_SIZE, "IPC handle size");
+
+RRError rrCudaExportDeviceMemory(RRContext context, RRDevicePtr device_ptr, void* handle_out, size_t* offset_out)
+{
+    if (!context || !device_ptr || !handle_out || !offset_out) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        RR_CUDA_CHECK(cudaSetDevice(C(context)->dev.device));
+        // the handle names the whole allocation: find its base through the driver (cuMemGetAddressRange)
+        using RangeFn = int (*)(unsigned long long*, size_t*, unsigned long long);
+        static RangeFn range = [] {
+            void* f = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+            return reinterpret_cast<RangeFn>(f);
+        }();
+        char*              p    = D(device_ptr)->ptr();
+        unsigned long long base = reinterpret_cast<unsigned long long>(p);
+        size_t             size = 0;
+        if (!range || range(&base, &size, reinterpret_cast<unsigned long long>(p)) != 0) throw std::runtime_error("cuMemGetAddressRange failed");
+        cudaIpcMemHandle_t h;
+        RR_CUDA_CHECK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+        std::memcpy(handle_out, &h, sizeof(h));
+        *offset_out = static_cast<size_t>(reinterpret_cast<unsigned long long>(p) - base);
+    }
+    catch (...) { return map_exception(); }
+    return RR_SUCCESS;
+}
+
+RRError rrCudaImportDeviceMemory(RRContext context, const void* handle, size_t offset, RRDevicePtr* device_ptr)
+{
+    if (!context || !handle || !device_ptr) return RR_ERROR_INVALID_PARAMETER;
+    try
+    {
+        RR_CUDA_CHECK(cudaSetDevice(C(context)->dev.device));
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle, sizeof(h));
+        void* mapped = nullptr;
+        RR_CUDA_CHECK(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+        DevicePtr* p = new DevicePtr;
+        p->base      = static_cast<char*>(mapped);
+        p->offset    = offset;
+        p->imported  = true;
+        *device_ptr  = reinterpret_cast<RRDevicePtr>(p);
     }
     catch (...) { return map_exception(); }
     return RR_SUCCESS;

@@ -1,18 +1,25 @@
 """Multi-GPU plumbing for the trace path (no reference counterpart -- RadeonRays is single GPU).
 
-Rays are independent units, so a batch shards into contiguous slices (keeps primary-ray coherence), one per rank;
-every rank needs the whole BVH.  A BLAS holds node INDICES, not pointers, so the bytes built on one rank are valid
-on every other: broadcast them once (NCCL over NVLink on the GPU box, gloo in the CPU tests) instead of rebuilding.
-Hits are gathered back with one all_gather.  There is no collective inside the traversal itself.
+Rays are independent units, so a batch shards into contiguous slices (keeps primary-ray coherence), one per rank; every rank
+needs the whole BVH.  A BLAS holds node INDICES, not pointers, and a scene buffer describes itself, so the bytes built on one rank
+are valid on every other: broadcast them once (NCCL over NVLink on the GPU box, gloo in the CPU tests) instead of rebuilding; a
+scene additionally gets its instance records re-pointed at the local copy of the geometry (rrCudaCmdRebindSceneGeometry).
+
+Hits come back in one of two ways:
+  * PeerHitBuffer (the product path on a GPU box): the destination buffer lives on the root rank and is mapped into every other
+    rank's address space (rrCudaExportDeviceMemory / rrCudaImportDeviceMemory = CUDA IPC + NVLink peer access).  Rank r passes
+    `buffer.slice_ptr(r)` as the `hits` argument of rrCmdIntersect and the traversal kernels store each hit straight into the
+    root's memory while they trace: compute and gather are one kernel, there is no staging buffer and no separate collective.
+  * gather_hits: trace into a local buffer, then one NCCL / gloo collective -- the comparison arm of bench.py and the CPU tests.
 """
 import numpy as np
 import torch
 import torch.distributed as dist
 
 
-def shard_range(count, rank, world, granule=32):
-    """Contiguous [begin, end) slice of `count` rays for `rank`; slice boundaries are multiples of `granule`
-    (a warp's worth of rays) so that no warp straddles two ranks' data."""
+def shard_range(count, rank, world, granule=64):
+    """Contiguous [begin, end) slice of `count` rays for `rank`; slice boundaries are multiples of `granule` (a packet's worth of
+    rays, rr_trace.cu k_trace_packet) so that no warp straddles two ranks' data."""
     per = -(-count // world)
     per = -(-per // granule) * granule
     begin = min(count, rank * per)
@@ -20,7 +27,7 @@ def shard_range(count, rank, world, granule=32):
 
 
 def broadcast_bytes(tensor, src=0):
-    """Broadcast a built BLAS (uint8 tensor, device or host) from `src` to every rank, in place."""
+    """Broadcast a built BLAS / scene (uint8 tensor, device or host) from `src` to every rank, in place."""
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.broadcast(tensor, src=src)
     return tensor
@@ -48,3 +55,46 @@ def trace_sharded(trace_fn, rays, item_bytes=16):
     b, e = shard_range(rays.shape[0], rank, world)
     local = trace_fn(rays[b:e])
     return gather_hits(local, rays.shape[0], item_bytes)
+
+
+class PeerHitBuffer:
+    """`total_bytes` of device memory on rank `root`, mapped into every rank.  ptr(byte_offset) is an RRDevicePtr usable as the
+    `hits` argument of rrCmdIntersect on the calling rank (local memory on the root, NVLink peer memory elsewhere)."""
+
+    def __init__(self, ctx, total_bytes, root=0):
+        self.ctx, self.root, self.total = ctx, root, int(total_bytes)
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self._ptrs = []
+        if self.rank == root:
+            self.base = ctx.allocate(self.total)            # cudaMalloc inside the library: a whole allocation, exportable
+            blob = [ctx.export_memory(self.base)]
+        else:
+            self.base, blob = None, [None]
+        if self.world > 1:
+            dist.broadcast_object_list(blob, src=root)
+        if self.rank != root:
+            handle, offset = blob[0]
+            self.base = ctx.import_memory(handle, offset)
+        self.address = ctx.raw_address(self.base)
+
+    def ptr(self, byte_offset=0):
+        p = self.ctx.device_ptr(self.address, int(byte_offset))
+        self._ptrs.append(p)
+        return p
+
+    def read(self, dtype=np.uint8):
+        """Root only: the buffer's current contents as a numpy array (rrMapDevicePtr / rrUnmapDevicePtr)."""
+        assert self.rank == self.root
+        arr, m = self.ctx.map(self.base, self.total, np.uint8)
+        out = np.array(arr, copy=True).view(dtype)
+        self.ctx.unmap(self.base, m)
+        return out
+
+    def close(self):
+        for p in self._ptrs:
+            self.ctx.release_ptr(p)
+        self._ptrs = []
+        if self.base is not None:
+            self.ctx.release_ptr(self.base)
+            self.base = None

@@ -37,26 +37,11 @@ def assert_hits_equal(got, want, rel_uv=1e-6, what="hits", mesh=None, rays=None)
 
 
 def pow2_scaled_rays(rays, max_shift=12):
-    """Rays whose direction components all have magnitude >= 1, made from `rays` by multiplying each direction by a power
-    of two (and dividing min_t / max_t by it): binary32 arithmetic scales exactly, so the hit triangle, uv and t * 2^m are
-    unchanged bit for bit.  Needed to compare with the reference's bvh_analyzer: its safe reciprocal calls an unqualified
-    `abs` (bvh_analyzer/float3.h:164-166) which g++ resolves to the INTEGER overload, so any |component| < 1 is treated as
-    zero and the ray's slab tests go wrong; with every |component| >= 1 its rcp is the shader's safe_invdir
-    (common.h:166-183).  Rays with a zero component (or needing more than max_shift doublings) are dropped.
-    -> (scaled rays, indices of the kept rays)"""
-    d = rays["direction"]
-    a = np.abs(d).min(1)
-    ok = a > 0
-    m = np.zeros(rays.shape[0], np.int32)
-    m[ok] = np.maximum(0, np.ceil(-np.log2(a[ok].astype(np.float64)))).astype(np.int32)
-    ok &= m <= max_shift
-    r = rays[ok].copy()
-    s = np.exp2(m[ok]).astype(np.float32)
-    r["direction"] *= s[:, None]
-    r["min_t"] /= s
-    r["max_t"] /= s
+    """See radeonrays_sdk_b200.workloads.pow2_scaled_rays (every |direction component| >= 1, results unchanged bit for bit)."""
+    from radeonrays_sdk_b200.workloads import pow2_scaled_rays as f
+    r, kept = f(rays, max_shift)
     assert (np.abs(r["direction"]).min(1) >= 1).all()
-    return r, np.nonzero(ok)[0]
+    return r, kept
 
 
 def assert_matches_reference_tracer(hits, ref, what, max_mask_mismatch=4):

@@ -17,7 +17,7 @@ def test_shard_ranges_cover_and_align():
             spans = [sharding.shard_range(count, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == count
             for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
-                assert e0 == b1 and (b1 % 32 == 0 or b1 == count)
+                assert e0 == b1 and (b1 % 64 == 0 or b1 == count)
             assert sum(e - b for b, e in spans) == count
 
 
