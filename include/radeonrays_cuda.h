@@ -49,7 +49,9 @@ RR_API RRError rrGetCudaPtrFromDevicePtr(RRContext context, RRDevicePtr device_p
 typedef enum
 {
     RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND   = 1,
-    RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK = 2
+    RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK = 2,
+    /* test hook: caps the hand-over lists of the staged refit (0 = library default) so that tests can drive them into overflow */
+    RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY      = 3
 } RRCudaOption;
 RR_API RRError rrCudaSetOption(RRContext context, RRCudaOption option, int value);
 

@@ -24,15 +24,13 @@ struct Logger
     std::mutex mu;
     int        level = RR_LOG_LEVEL_WARN;
     FILE*      file  = nullptr;
+    Logger()
+    {
+        if (const char* e = std::getenv("RR_LOG_LEVEL")) level = std::atoi(e);
+    }
     static Logger& get()
     {
-        static Logger L;
-        static bool   init = false;
-        if (!init)
-        {
-            init = true;
-            if (const char* e = std::getenv("RR_LOG_LEVEL")) L.level = std::atoi(e);
-        }
+        static Logger L;  // thread-safe initialisation (C++11 magic static)
         return L;
     }
     void log(int lvl, const char* fmt, ...)
@@ -105,9 +103,13 @@ struct Context
     uint64_t     launches   = 0;
     bool         first_found_tie_rule   = false;
     bool         reference_corner_quirk = false;
+    // Kernels cannot throw: conditions they cannot handle (a traversal stack deeper than the deep kernel's arena, an emission
+    // hand-over list longer than its slots) OR a bit into this host-mapped word, and rrWaitEvent turns it into RR_ERROR_INTERNAL.
+    volatile uint32_t* host_error = nullptr;
     ~Context()
     {
         if (own_stream && stream) cudaStreamDestroy(stream);
+        if (host_error) cudaFreeHost(const_cast<uint32_t*>(host_error));
     }
 };
 
@@ -137,6 +139,15 @@ static RRError create_context(int device, void* stream, RRContext* out)
     ctx->dev.sm_count = prop.multiProcessorCount;
     ctx->dev.l2_bytes = (size_t)prop.l2CacheSize;
     ctx->dev.launches = &ctx->launches;
+    {
+        void* h = nullptr;
+        RR_CUDA_CHECK(cudaHostAlloc(&h, 64, cudaHostAllocMapped));
+        std::memset(h, 0, 64);
+        ctx->host_error = static_cast<volatile uint32_t*>(h);
+        void* d = nullptr;
+        RR_CUDA_CHECK(cudaHostGetDevicePointer(&d, h, 0));
+        ctx->dev.error_word = static_cast<uint32_t*>(d);
+    }
     if (stream) ctx->stream = static_cast<cudaStream_t>(stream);
     else
     {
@@ -156,6 +167,14 @@ static inline Event*         E(RREvent e) { return reinterpret_cast<Event*>(e); 
 // The kernels use 16- and 32-byte vector accesses: node arrays (geometry / scene buffers) must be 64-byte aligned, ray, hit
 // and temporary buffers 16-byte aligned (every cudaMalloc'ed buffer is; an interop pointer + offset may not be).
 static bool aligned_to(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+// A context may live on the client's own stream (rrCreateContextCuda): if the client is capturing that stream into a graph of
+// its own, the library must not begin a second capture on it -- its commands are then simply recorded into the client's graph.
+static bool client_is_capturing(cudaStream_t s)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+}
 
 static bool wants_restructure(const RRBuildOptions* o)
 {   // vlk/intersector.cpp:116-119,170
@@ -432,12 +451,12 @@ RRError rrSumbitCommandStream(RRContext context, RRCommandStream command_stream,
         if (wait_event) RR_CUDA_CHECK(cudaStreamWaitEvent(cs->stream, E(wait_event)->ev, 0));
         static const bool graphs = [] { const char* e = std::getenv("RR_CUDA_GRAPHS"); return !e || std::atoi(e) != 0; }();
         ++cs->submits;
-        if (graphs && cs->graphable && !cs->external && cs->exec && cs->captured_commands == cs->commands.size())
+        if (graphs && cs->graphable && !cs->external && cs->exec && cs->captured_commands == cs->commands.size() && !client_is_capturing(cs->stream))
         {
             RR_CUDA_CHECK(cudaGraphLaunch(cs->exec, cs->stream));
             ctx->launches += cs->captured_launches;
         }
-        else if (graphs && cs->graphable && !cs->external && cs->submits >= 2 && !cs->commands.empty())
+        else if (graphs && cs->graphable && !cs->external && cs->submits >= 2 && !cs->commands.empty() && !client_is_capturing(cs->stream))
         {   // (re)capture: the closures issue exactly the work a plain submit would
             if (cs->exec) { cudaGraphExecDestroy(cs->exec); cs->exec = nullptr; }
             const uint64_t l0 = ctx->launches;
@@ -490,6 +509,15 @@ RRError rrWaitEvent(RRContext context, RREvent event)
     if (!context || !event) return RR_ERROR_INVALID_PARAMETER;
     try { RR_CUDA_CHECK(cudaEventSynchronize(E(event)->ev)); }
     catch (...) { return map_exception(); }
+    Context* ctx = C(context);
+    if (ctx->host_error && *ctx->host_error)
+    {
+        const uint32_t bits = *ctx->host_error;
+        *ctx->host_error    = 0;
+        RR_ERR("device-side error bits 0x%x: %s%s", bits, (bits & kErrorTraceStackOverflow) ? "traversal stack deeper than the deep kernel's arena; " : "",
+               (bits & kErrorEmitListOverflow) ? "hierarchy emission hand-over list overflow" : "");
+        return RR_ERROR_INTERNAL;
+    }
     return RR_SUCCESS;
 }
 
@@ -600,6 +628,7 @@ RRError rrCudaSetOption(RRContext context, RRCudaOption option, int value)
     {
     case RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND: C(context)->first_found_tie_rule = value != 0; return RR_SUCCESS;
     case RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK: C(context)->reference_corner_quirk = value != 0; return RR_SUCCESS;
+    case RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY: C(context)->dev.refit_list_capacity = value > 0 ? (uint32_t)value : 0u; return RR_SUCCESS;
     default: return RR_ERROR_INVALID_PARAMETER;
     }
 }

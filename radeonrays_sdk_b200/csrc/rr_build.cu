@@ -19,6 +19,8 @@
 
 #include <cuda.h>  // CUtensorMap (encoded through the runtime's driver entry point: libcuda is not linked)
 
+#include <mutex>
+
 #include "rr_internal.h"
 
 namespace rr
@@ -229,6 +231,8 @@ struct EmitParams
     uint8_t*        deltas;  // [n] delta(j, j+1) per sorted leaf in the geometry buffer's tail: written by a build, read by a refit
     uint32_t*       karras;      // tail header word: 1 while the tree is Karras-numbered (cleared by the treelet restructuring)
     bool            from_tail;   // refit: codes == nullptr, deltas / refs come from the tail; run only if *karras == 1
+    uint32_t*       error;     // DeviceInfo::error_word (kErrorEmitListOverflow)
+    bool            prefetch;  // k_emit_window pulls the node images of its first pass into L2 before it merges
     bool            tma;     // k_emit_leaves stages node images in shared memory and stores them with TMA tensor copies
     uint32_t*       masks;             // [ceil(n/32)] per 32 leaves: left ends of the subtrees k_emit_leaves left over
     // mesh leaves
@@ -696,6 +700,16 @@ __global__ void __launch_bounds__(32 * kWindowWarps, 5) k_emit_window(EmitParams
     };
     auto left_end = [&](int r) -> int { return b0 + (int)list[min(r, M)]; };
     load_masks();
+    if (p.prefetch)
+    {   // the first pass reads back ~100 node images k_emit_leaves wrote (long out of L2 on a large mesh), group after group with a
+        // dependent merge in between: ask for all of them now
+        for (int e = lane; e < M; e += 32)
+        {
+            const int a = left_end(e), b = left_end(e + 1) - 1;
+            const uint32_t id = a == b ? (uint32_t)(leaf0 + a) : (uint32_t)(delta_adj(b) > delta_adj(a - 1) ? b : a);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.nodes + id));
+        }
+    }
     auto direct_store = [&](uint32_t idx, float4 q0, float4 q1, float4 q2, float4 q3) { st_node(p.nodes + idx, q0, q1, q2, q3); };
     bool prev_formed = true;
     for (int pass = 1; M > 1 && pass < kEmitMaxPasses; ++pass)
@@ -738,7 +752,11 @@ __global__ void __launch_bounds__(32 * kWindowWarps, 5) k_emit_window(EmitParams
 
     // ---- what is left has its sibling outside the window: the next level (k_emit_upper) continues from the list of left ends
     uint32_t* out = p.lists + (size_t)w * kListStride;
-    if (lane == 0) out[0] = (uint32_t)min(M, kListSlots);
+    if (lane == 0)
+    {
+        out[0] = (uint32_t)min(M, kListSlots);
+        if (M > kListSlots) atomicOr(p.error, kErrorEmitListOverflow);  // (at most 2 per tree level can be left: never seen)
+    }
     for (int e = lane; e < min(M, kListSlots); e += 32) out[1 + e] = (uint32_t)left_end(e);
 }
 
@@ -883,6 +901,42 @@ __global__ void __launch_bounds__(32 * kUpperWarps) k_emit_upper(EmitParams p, c
 // the node writes with short-lived CTAs, stage 2 (6 levels) most of the rest, stage 3 the O(n/512) long climbs to the
 // root.  In a single kernel every CTA stayed resident until its one long climber reached the root and the SMs ran
 // mostly empty (8.2 ms for 50 M triangles, 16 % of the HBM roofline).
+// Finishes the refit of the ancestors of the complete subtree `me` on the spot, with the parity rendezvous of k_refit<false>
+// (the node's `update` word counts arrivals; the second one writes the parent).  The staged refit kernels fall back to this when
+// a hand-over list is full, so that a list sized for the common case can never lose a subtree (stale boxes would mean silently
+// missed hits).
+__device__ __forceinline__ void refit_climb_in_place(Node* __restrict__ nodes, int leaf0, uint32_t me)
+{
+    __threadfence();
+    const float4* np = reinterpret_cast<const float4*>(nodes + me);
+    const float4  q0 = __ldcg(np), q1 = __ldcg(np + 1), q2 = __ldcg(np + 2), q3 = __ldcg(np + 3);
+    float3 lo, hi;
+    node_box(q0, q1, q2, q3, me >= (uint32_t)leaf0, lo, hi);
+    uint32_t parent = wbits(q2);
+    while (parent != kInvalid)
+    {
+        __threadfence();
+        const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(nodes + parent) + 15, 1u);
+        if ((old & 1u) == 0) break;
+        __threadfence();
+        float4* pp = reinterpret_cast<float4*>(nodes + parent);
+        const float4 p0 = __ldcg(pp), p1 = __ldcg(pp + 1), p2 = __ldcg(pp + 2);
+        const uint32_t c0 = wbits(p0), c1 = wbits(p1), up = wbits(p2);
+        const bool     is_left = (c0 == me);
+        const uint32_t sib = is_left ? c1 : c0;
+        const float4*  sp = reinterpret_cast<const float4*>(nodes + sib);
+        const float4   s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2), s3 = __ldcg(sp + 3);
+        float3 slo, shi;
+        node_box(s0, s1, s2, s3, sib >= (uint32_t)leaf0, slo, shi);
+        if (is_left) { pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up); pp[3] = pack(shi, old + 1u); }
+        else { pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up); pp[3] = pack(hi, old + 1u); }
+        lo = min3(lo, slo);
+        hi = max3(hi, shi);
+        me = parent;
+        parent = up;
+    }
+}
+
 struct RefitLists
 {
     uint32_t* count_a;   // stage 1 -> 2
@@ -983,7 +1037,11 @@ __global__ void __launch_bounds__(256)
                 s_base = s_n ? atomicAdd(out_count, s_n) : 0u;
             }
             __syncthreads();
-            if (threadIdx.x < s_n && s_base + threadIdx.x < capacity) out_items[s_base + threadIdx.x] = s_list[threadIdx.x];
+            if (threadIdx.x < s_n)
+            {
+                if (s_base + threadIdx.x < capacity) out_items[s_base + threadIdx.x] = s_list[threadIdx.x];
+                else refit_climb_in_place(nodes, (int)leaf0, s_list[threadIdx.x]);  // full list: finish here, never drop
+            }
             __syncthreads();
             if (threadIdx.x == 0) s_n = 0;
             __syncthreads();
@@ -1041,36 +1099,7 @@ __global__ void __launch_bounds__(256, 4)  // 64 registers; 3 / 5 / 6 CTAs per S
     };
     // appends this warp's finished-but-waiting subtrees (up to two per lane) to the stage-2 list with one atomic; a full list
     // (adversarial topologies only) makes the lane finish the climb here with the parity rendezvous
-    auto climb_here = [&](uint32_t me) {
-        __threadfence();
-        const float4* np = reinterpret_cast<const float4*>(nodes + me);
-        const float4  q0 = __ldcg(np), q1 = __ldcg(np + 1), q2 = __ldcg(np + 2), q3 = __ldcg(np + 3);
-        float3 lo, hi;
-        node_box(q0, q1, q2, q3, me >= (uint32_t)leaf0, lo, hi);
-        uint32_t parent = wbits(q2);
-        while (parent != kInvalid)
-        {
-            __threadfence();
-            const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(nodes + parent) + 15, 1u);
-            if ((old & 1u) == 0) break;
-            __threadfence();
-            float4* pp = reinterpret_cast<float4*>(nodes + parent);
-            const float4 p0 = __ldcg(pp), p1 = __ldcg(pp + 1), p2 = __ldcg(pp + 2);
-            const uint32_t c0 = wbits(p0), c1 = wbits(p1), up = wbits(p2);
-            const bool     is_left = (c0 == me);
-            const uint32_t sib = is_left ? c1 : c0;
-            const float4*  sp = reinterpret_cast<const float4*>(nodes + sib);
-            const float4   s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2), s3 = __ldcg(sp + 3);
-            float3 slo, shi;
-            node_box(s0, s1, s2, s3, sib >= (uint32_t)leaf0, slo, shi);
-            if (is_left) { pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up); pp[3] = pack(shi, old + 1u); }
-            else { pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up); pp[3] = pack(hi, old + 1u); }
-            lo = min3(lo, slo);
-            hi = max3(hi, shi);
-            me = parent;
-            parent = up;
-        }
-    };
+    auto climb_here = [&](uint32_t me) { refit_climb_in_place(nodes, leaf0, me); };
     auto hand_over = [&](bool over_a, uint32_t id_a, bool over_b, uint32_t id_b) {
         const uint32_t ma = __ballot_sync(full, over_a), mb = __ballot_sync(full, over_b);
         if ((ma | mb) == 0) return;
@@ -1277,7 +1306,10 @@ __global__ void __launch_bounds__(256)
     if (lane == 0 && M > 0) base = atomicAdd(out_count, (uint32_t)M);
     base = __shfl_sync(full, base, 0);
     for (int e = lane; e < M; e += 32)
+    {
         if (base + e < capacity) out_items[base + e] = s_list[wi][cur][e];
+        else refit_climb_in_place(nodes, leaf0, s_list[wi][cur][e]);  // full list: finish here, never drop
+    }
 }
 
 // ---- K8: instance world boxes + scene AABB (lbvh_calc_scene_aabb.comp:131-163, common.h:270-308) -------
@@ -1361,18 +1393,20 @@ int launch_emit_fit(const DeviceInfo& dev, cudaStream_t s, const EmitParams& p_i
     EmitParams  p = p_in;
     CUtensorMap tm_leaf{}, tm_node{};
     static const bool tma_allowed = [] { const char* e = std::getenv("RR_CUDA_EMIT_TMA"); return !e || std::atoi(e) != 0; }();
+    static const bool prefetch_allowed = [] { const char* e = std::getenv("RR_CUDA_EMIT_PREFETCH"); return !e || std::atoi(e) != 0; }();
+    p.prefetch = prefetch_allowed;
+    p.error    = dev.error_word;
     p.tma = !kScene && tma_allowed && p.n >= 2 && node_tensor_map(&tm_leaf, p.nodes + (p.n - 1), p.n) && node_tensor_map(&tm_node, p.nodes, p.n - 1);
     if (p.from_tail) k_emit_leaves<kScene, true><<<ctas, 256, 0, s>>>(p, tm_leaf, tm_node);
     else k_emit_leaves<kScene, false><<<ctas, 256, 0, s>>>(p, tm_leaf, tm_node);
     if (p.n <= 32) return 1;  // the whole tree was inside one group
     k_emit_window<kScene><<<(windows + kWindowWarps - 1) / kWindowWarps, 32 * kWindowWarps, 0, s>>>(p);
     int launches = 2;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
+    // once per device and thread-safe: contexts on different devices / threads share this code (radeonrays.h:267-270)
+    static std::once_flag attr_once[kMaxDevices];
+    std::call_once(attr_once[dev.device % kMaxDevices], [] {
         RR_CUDA_CHECK(cudaFuncSetAttribute(k_emit_upper<kScene>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpperSmem)));
-        attr_set = true;
-    }
+    });
     // upper levels: kUpperFan windows of the level below per CTA, lists ping-pong between the two halves of the list area
     uint32_t  num = windows, leaves_per = (uint32_t)kEmitWindow;
     uint32_t* in  = p.lists;
@@ -1477,6 +1511,10 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
 // Update scratch: [256 B: the two list counters | list A 4 x capacity | list B 4 x capacity], capacity = n/4 + 256:
 // a hand-over after k levels implies a finished subtree of >= k+1 leaves, so stage 1 (3 levels) emits <= n/4 entries.
 constexpr uint32_t kRefitWarpPathMin = 500000u;  // triangles from which the generic stages 1 / 2 are the warp-cooperative kernels
+// Stage-3 list of the warp-cooperative path: a 32-leaf group hands at most kRefitSlots - 1 subtrees to its window, and a window
+// passes on at most what it was handed, so (kRefitSlots - 1) entries per group can never overflow, whatever the topology
+// (a treelet-restructured tree pairs far fewer siblings inside a window than a Karras tree does).
+static uint32_t refit_warp_capacity(uint32_t n) { return (kRefitSlots - 1) * ((n + 31) / 32) + 256; }
 // Scratch of the re-emission path: [256 B | one mask per 32 leaves | per-window lists], as in the build.
 static size_t reemit_scratch_size(uint32_t n) { return 256 + align_up(sizeof(uint32_t) * (((size_t)n + 31) / 32), 256) + align_up(emit_list_bytes(n), 256); }
 size_t update_scratch_size(uint32_t n)
@@ -1484,7 +1522,7 @@ size_t update_scratch_size(uint32_t n)
     const size_t cap = (size_t)n / 4 + 256;
     size_t generic;
     if (n >= kRefitWarpPathMin)  // counters | stage-3 list | 16 words per 32-leaf group between k_refit_leaves and k_refit_window
-        generic = 256 + align_up(sizeof(uint32_t) * cap, 256) + align_up(sizeof(uint32_t) * kRefitSlots * (((size_t)n + 31) / 32), 256);
+        generic = 256 + align_up(sizeof(uint32_t) * (size_t)refit_warp_capacity(n), 256) + align_up(sizeof(uint32_t) * kRefitSlots * (((size_t)n + 31) / 32), 256);
     else
         generic = 256 + 2 * align_up(sizeof(uint32_t) * cap, 256);
     return std::max(generic, reemit_scratch_size(n));
@@ -1523,7 +1561,8 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
         p.lists = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (((size_t)n + 31) / 32), 256));
         *dev.launches += launch_emit_fit<false>(dev, s, p);
     }
-    const uint32_t cap = n / 4 + 256;
+    // (a debug option shrinks the lists so that tests can drive the hand-overs into their in-place fallback)
+    const uint32_t cap = dev.refit_list_capacity ? std::min<uint32_t>(dev.refit_list_capacity, n / 4 + 256) : n / 4 + 256;
     RefitLists L;
     L.count_a = reinterpret_cast<uint32_t*>(sc);
     L.count_b = L.count_a + 1;
@@ -1541,15 +1580,16 @@ void update_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, No
     {   // large meshes: warp-cooperative stages 1 (per 32 leaves) and 2 (per 512-leaf window), then the parity-rendezvous climb
         // for the ~2 % that is left.  For small ones the pipeline prologue of the persistent kernel costs more than it hides
         // (Sponza, 262 k triangles: 0.150 against 0.133 ms).
-        uint32_t* slots = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (size_t)cap, 256));
+        const uint32_t wcap  = dev.refit_list_capacity ? std::min<uint32_t>(dev.refit_list_capacity, refit_warp_capacity(n)) : refit_warp_capacity(n);
+        uint32_t*      slots = reinterpret_cast<uint32_t*>(sc + 256 + align_up(sizeof(uint32_t) * (size_t)refit_warp_capacity(n), 256));
         CUtensorMap tm_leaf{};
         const int   tma = node_tensor_map(&tm_leaf, nodes + (n - 1), n) ? 1 : 0;
         k_refit_leaves<<<std::min<uint32_t>((n + 255) / 256, (uint32_t)dev.sm_count * 4u), 256, 0, s>>>(mesh, nodes, n, slots, L.count_a, L.items_a,
-                                                                                                   cap, tm_leaf, tma, karras);
+                                                                                                   wcap, tm_leaf, tma, karras);
         const uint32_t windows = (n + kEmitWindow - 1) / kEmitWindow;
-        k_refit_window<<<(windows + 7) / 8, 256, 0, s>>>(nodes, n, slots, L.count_a, L.items_a, cap, karras);
-        const uint32_t grid3 = std::min<uint32_t>((cap + 255) / 256, (uint32_t)dev.sm_count * 32u);
-        k_refit<false><<<grid3, 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, kUnbounded, nullptr, nullptr, cap, karras);
+        k_refit_window<<<(windows + 7) / 8, 256, 0, s>>>(nodes, n, slots, L.count_a, L.items_a, wcap, karras);
+        const uint32_t grid3 = std::min<uint32_t>((n / 4 + 511) / 256, (uint32_t)dev.sm_count * 32u);
+        k_refit<false><<<grid3, 256, 0, s>>>(mesh, nodes, n, L.count_a, L.items_a, kUnbounded, nullptr, nullptr, wcap, karras);
         *dev.launches += 3;
     }
     else

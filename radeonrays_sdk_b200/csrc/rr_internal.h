@@ -23,8 +23,11 @@
 
 namespace rr
 {
+constexpr int      kMaxDevices = 64;  // per-device one-time initialisation flags
 constexpr uint32_t kInvalid  = 0xFFFFFFFFu;
 constexpr uint32_t kSentinel = 0xFFFFFFFEu;  // isect_2l.comp RR_TOP_LEVEL_SENTINEL
+// bits of DeviceInfo::error_word
+constexpr uint32_t kErrorTraceStackOverflow = 1u, kErrorEmitListOverflow = 2u;
 
 // 64-byte BVH2 node, identical to the reference's layout (vlk/kernels/bvh2.h:25-35) so that a raw
 // dump of a geometry buffer is a VkBvhNode[] that bvh_analyzer can load (bvh_analyzer/transform.h:31-41).
@@ -95,6 +98,8 @@ struct DeviceInfo
     int      sm_count    = 148;
     size_t   l2_bytes    = 0;
     uint64_t* launches   = nullptr;  // per-context launch counter (host side)
+    uint32_t  refit_list_capacity = 0;  // test hook (RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY): 0 = sized by the library
+    uint32_t* error_word = nullptr;  // device-visible (host-mapped) word the kernels OR error bits into; checked by rrWaitEvent
 };
 
 // ---- sort (rr_sort.cu) ------------------------------------------------------------------------------

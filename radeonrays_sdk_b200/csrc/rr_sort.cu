@@ -11,6 +11,7 @@
 // HBM traffic per pair: histogram read 4 B (0 when fused) + 4 passes x (8 B read + 8 B write), minus the
 // 4-B value read of pass 0 when values are the identity.  Roofline: HBM bandwidth.
 #include <algorithm>
+#include <mutex>
 
 #include "rr_internal.h"
 
@@ -280,13 +281,11 @@ void sort_pairs(const DeviceInfo& dev, cudaStream_t s, const SortLayout& L, void
                 uint32_t* keys_out, uint32_t* vals_out)
 {
     if (L.n == 0) return;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
+    static std::once_flag attr_once[kMaxDevices];  // once per device, thread-safe (contexts may live on different threads)
+    std::call_once(attr_once[dev.device % kMaxDevices], [] {
         RR_CUDA_CHECK(cudaFuncSetAttribute(k_onesweep_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes));
         RR_CUDA_CHECK(cudaFuncSetAttribute(k_onesweep_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes));
-        attr_set = true;
-    }
+    });
     char*     sc       = (char*)scratch;
     uint32_t* hist     = reinterpret_cast<uint32_t*>(sc + L.hist_off);
     uint32_t* tickets  = reinterpret_cast<uint32_t*>(sc + L.counter_off);

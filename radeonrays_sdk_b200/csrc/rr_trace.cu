@@ -185,15 +185,17 @@ struct SmemStack
 // Stack of the deep kernel: kDeepStack entries per thread in the scratch arena, same [level][thread] layout (coalesced,
 // L1/L2 resident).  A radix tree over distinct (30-bit code, 32-bit index) keys is at most 62 levels deep and treelet
 // restructuring only permutes 7-leaf treelets, so kDeepStack = 192 covers TLAS + sentinel + BLAS with margin; a deeper
-// entry would be dropped rather than corrupt memory.
+// entry is not stored (memory stays intact) and sets kErrorTraceStackOverflow, which the next rrWaitEvent reports.
 struct DeepStack
 {
     uint32_t* base;  // &arena[thread slot]
     uint32_t  stride;
     int       sp;
+    uint32_t* error;  // DeviceInfo::error_word: an entry that does not fit is reported (rrWaitEvent -> RR_ERROR_INTERNAL), never silent
     __device__ __forceinline__ bool push(uint32_t v)
     {
         if (sp < kDeepStack) base[(size_t)sp * stride] = v;
+        else atomicOr(error, kErrorTraceStackOverflow);
         ++sp;
         return true;
     }
@@ -218,6 +220,7 @@ struct TraceParams
     uint32_t*             chunk_list;     // [ceil(ray_count / 32)] their chunk indices; nullptr: k_trace walks all chunks itself
     int                   first_found;
     int                   force_generic;
+    uint32_t*             error;          // DeviceInfo::error_word
 };
 
 // A geometry buffer starts with node 0, a scene buffer with a SceneHeader (rr_internal.h): every kernel checks on the device that
@@ -609,6 +612,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_deep(TraceParams P)
     DeepStack st;
     st.base   = P.arena + (blockIdx.x * kTraceThreads + threadIdx.x);
     st.stride = gridDim.x * kTraceThreads;
+    st.error  = P.error;
     while (true)
     {
         uint32_t chunk = 0;
@@ -681,6 +685,7 @@ void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
     uint32_t* chunk_list = P.overflow_list + overflow_list_bytes(a.ray_count) / sizeof(uint32_t);
     P.arena = chunk_list + chunk_list_bytes(a.ray_count) / sizeof(uint32_t);
     P.chunk_list = nullptr;
+    P.error = dev.error_word;
     static const int force_generic = [] { const char* e = std::getenv("RR_CUDA_TRACE_GENERIC"); return e ? std::atoi(e) : 0; }();
     static const int no_packets    = [] { const char* e = std::getenv("RR_CUDA_TRACE_PACKETS"); return e && std::atoi(e) == 0 ? 1 : 0; }();
     P.force_generic = force_generic;

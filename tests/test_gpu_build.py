@@ -239,3 +239,28 @@ def test_sort_pairs_stable(engine):
         assert np.array_equal(ov.cpu().numpy().view(np.uint32), vals[order])
         api.check(engine.ctx.lib.rrCudaDebugSortPairs(engine.ctx.handle, dk.data_ptr(), None, ok.data_ptr(), ov.data_ptr(), n))
         assert np.array_equal(ov.cpu().numpy().view(np.uint32), order.astype(np.uint32))
+
+
+@pytest.mark.parametrize("shape", ["sponza", "heightfield_540k"])
+def test_refit_hand_over_lists_never_drop_a_subtree(engine, sponza, shape):
+    """the staged refit hands finished subtrees from stage to stage through lists sized for the common
+    case; an entry past the capacity used to be discarded, leaving its ancestors stale.  Every hand-over now falls back to
+    finishing the climb in place.  RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY shrinks the lists to 64 entries so that almost every
+    hand-over overflows, on a treelet-restructured tree, for both the small-mesh stages (Sponza) and the warp-cooperative stages
+    (>= 500 000 triangles): the refitted tree must still equal the oracle's bit for bit."""
+    if shape == "sponza":
+        pos, idx, _ = sponza
+        moved = (pos * np.float32(1.25)).astype(np.float32)
+    else:
+        pos, idx = W.heightfield_mesh(600, 450, t=0.0)
+        moved, _ = W.heightfield_mesh(600, 450, t=1.0)
+    g = engine.build_geometry(pos, idx, build_flags=0)          # quality build: restructured, generic refit path
+    before = g.nodes()
+    engine.ctx.set_option(api.RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY, 64)
+    try:
+        engine.update_geometry(g, moved)
+    finally:
+        engine.ctx.set_option(api.RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY, 0)
+    assert_nodes_equal(g.nodes(), O.refit(before, moved, idx), what="refit with overflowing hand-over lists")
+    engine.update_geometry(g, pos)                              # and back, with the default capacities
+    assert_nodes_equal(g.nodes(), O.refit(before, pos, idx), what="refit back")
