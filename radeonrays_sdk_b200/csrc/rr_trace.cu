@@ -23,6 +23,7 @@
 // issue slots are the second limit (profiles/).
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 #include "rr_internal.h"
 
@@ -444,6 +445,9 @@ __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(Tra
 // ANY queries and RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND depend on the reference's visit order and stay on k_trace.
 // A packet whose 64 rays do not share a direction octant, or whose shared stack would overflow, is handed to k_trace through
 // the chunk list (two 32-ray chunks), which then runs in list mode right after this kernel.
+constexpr int      kTopLevels = 8;             // (experiment variant of k_trace_packet: levels of the tree staged in shared memory)
+constexpr int      kTopNodes  = (1 << kTopLevels) - 1;
+constexpr uint32_t kTopTag    = 0x80000000u;
 constexpr int      kPacketThreads = 128;
 constexpr int      kPacketStack   = 64;            // entries per warp; LBVH depth beyond that goes to k_trace / k_trace_deep
 
@@ -476,22 +480,31 @@ __device__ __forceinline__ void write_closest(const TraceParams& P, uint32_t gid
 // node (their arithmetic interleaves), a lane without a ray carries closest = -FLT_MAX so that no test of it can pass, one
 // predicate per child ("any of my two rays wants it") feeds one VOTE.ANY, the near child is the one most lanes' slot-0 rays
 // enter first, and the stack is addressed through a 32-bit shared-memory address.
-template <bool kFullHit, int kOct>
+template <bool kFullHit, int kOct, bool kTop>
 __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stack_lo, const uint32_t (&gidx)[2], const bool (&valid)[2],
-                                             const float4 (&r0)[2], const float4 (&r1)[2], const RayState (&ray)[2])
+                                             const float4 (&r0)[2], const float4 (&r1)[2], const RayState (&ray)[2], const float4* s_top,
+                                             const uint32_t* s_top_id)
 {
     const float kNever = -3.402823466e+38f;
     float    closest[2]      = {valid[0] ? r1[0].w : kNever, valid[1] ? r1[1].w : kNever};
     uint32_t closest_addr[2] = {kInvalid, kInvalid}, closest_prim[2] = {kInvalid, kInvalid};
     uint32_t sp  = stack_lo;                                   // shared-memory byte address of the next free entry
     const uint32_t stack_hi = stack_lo + kPacketStack * 4;
-    uint32_t cur = 0;
+    uint32_t cur = kTop ? kTopTag : 0u;  // the root (slot 0 of the staged top when kTop)
     while (true)
     {
-        const float4* np = reinterpret_cast<const float4*>(P.bvh + cur);
         float4 q0, q1, q2, q3;
-        ldg_half_node(np, q0, q1);
-        ldg_half_node(np + 2, q2, q3);
+        if (kTop && (cur & kTopTag))
+        {   // experiment: the top levels of the tree staged in shared memory (see k_trace_packet)
+            const float4* sp = s_top + 4 * (cur & ~kTopTag);
+            q0 = sp[0]; q1 = sp[1]; q2 = sp[2]; q3 = sp[3];
+        }
+        else
+        {
+            const float4* np = reinterpret_cast<const float4*>(P.bvh + cur);
+            ldg_half_node(np, q0, q1);
+            ldg_half_node(np + 2, q2, q3);
+        }
         if (wbits(q0) != kInvalid)
         {
             float a0, a1, b0, b1, c0, c1, d0, d1;
@@ -537,15 +550,53 @@ __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stac
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k)
+    {
+        if (kTop && closest_addr[k] != kInvalid && (closest_addr[k] & kTopTag)) closest_addr[k] = s_top_id[closest_addr[k] & ~kTopTag];
         if (valid[k]) write_closest<kFullHit>(P, gidx[k], r0[k], r1[k], closest[k], closest_addr[k], closest_prim[k]);
+    }
     return true;
 }
 
-template <bool kFullHit>
-__global__ void __launch_bounds__(kPacketThreads, 7) k_trace_packet(TraceParams P)
+// kTop (experiment, RR_CUDA_PACKET_TOP_LEVELS=1; north_star: "staging of top BVH levels"): every CTA first copies the top
+// kTopLevels levels of the tree (255 nodes, 16 KB) into shared memory in heap order -- slot s holds a node, its children sit in
+// slots 2s+1 / 2s+2 and the staged child words are rewritten to tagged slot numbers -- and the traversal reads tagged nodes with
+// LDS instead of LDG.  Measured on C2 (profiles/round2_summary.md): slower than the plain kernel; the top of the tree is the part
+// that always hits in L1 anyway, an L1 hit costs 32 clk against 29 for LDS, the 16 KB per CTA come out of the L1 capacity the
+// lower levels need, and the tag test adds instructions to a loop that is bound by issue slots.  Off by default.
+template <bool kFullHit, bool kTop>
+__global__ void __launch_bounds__(kPacketThreads, 8) k_trace_packet(TraceParams P)
 {
     __shared__ uint32_t s_stack[(kPacketThreads / 32) * kPacketStack];
+    extern __shared__ float4 s_dyn[];
+    float4*   s_top    = s_dyn;
+    uint32_t* s_top_id = reinterpret_cast<uint32_t*>(s_dyn + 4 * kTopNodes);
     if (!resolve_scene<false>(P)) return;
+    if (kTop)
+    {
+        for (int i = threadIdx.x; i < kTopNodes; i += kPacketThreads) s_top_id[i] = i == 0 ? 0u : kInvalid;
+        __syncthreads();
+        for (int level = 0; level < kTopLevels; ++level)
+        {
+            const int first = (1 << level) - 1, width = 1 << level;
+            for (int i = threadIdx.x; i < width; i += kPacketThreads)
+            {
+                const int      slot = first + i;
+                const uint32_t id   = s_top_id[slot];
+                if (id == kInvalid) continue;
+                const float4* np = reinterpret_cast<const float4*>(P.bvh + id);
+                float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+                if (wbits(q0) != kInvalid && level + 1 < kTopLevels)
+                {
+                    s_top_id[2 * slot + 1] = wbits(q0);
+                    s_top_id[2 * slot + 2] = wbits(q1);
+                    q0.w = __uint_as_float(kTopTag | (uint32_t)(2 * slot + 1));
+                    q1.w = __uint_as_float(kTopTag | (uint32_t)(2 * slot + 2));
+                }
+                s_top[4 * slot] = q0; s_top[4 * slot + 1] = q1; s_top[4 * slot + 2] = q2; s_top[4 * slot + 3] = q3;
+            }
+            __syncthreads();
+        }
+    }
     uint32_t count = P.ray_count;
     if (P.indirect) count = min(count, __ldg(P.indirect));
     const uint32_t lane  = threadIdx.x & 31;
@@ -580,14 +631,14 @@ __global__ void __launch_bounds__(kPacketThreads, 7) k_trace_packet(TraceParams 
         {
             switch (oct0)
             {
-            case 0: done = trace_packet<kFullHit, 0>(P, stack, gidx, valid, r0, r1, ray); break;
-            case 1: done = trace_packet<kFullHit, 1>(P, stack, gidx, valid, r0, r1, ray); break;
-            case 2: done = trace_packet<kFullHit, 2>(P, stack, gidx, valid, r0, r1, ray); break;
-            case 3: done = trace_packet<kFullHit, 3>(P, stack, gidx, valid, r0, r1, ray); break;
-            case 4: done = trace_packet<kFullHit, 4>(P, stack, gidx, valid, r0, r1, ray); break;
-            case 5: done = trace_packet<kFullHit, 5>(P, stack, gidx, valid, r0, r1, ray); break;
-            case 6: done = trace_packet<kFullHit, 6>(P, stack, gidx, valid, r0, r1, ray); break;
-            default: done = trace_packet<kFullHit, 7>(P, stack, gidx, valid, r0, r1, ray); break;
+            case 0: done = trace_packet<kFullHit, 0, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
+            case 1: done = trace_packet<kFullHit, 1, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
+            case 2: done = trace_packet<kFullHit, 2, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
+            case 3: done = trace_packet<kFullHit, 3, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
+            case 4: done = trace_packet<kFullHit, 4, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
+            case 5: done = trace_packet<kFullHit, 5, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
+            case 6: done = trace_packet<kFullHit, 6, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
+            default: done = trace_packet<kFullHit, 7, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
             }
         }
         if (!done && lane == 0)
@@ -669,7 +720,7 @@ size_t trace_scratch_size(const DeviceInfo& dev, uint32_t ray_count)
 static int packet_ctas_per_sm()
 {
     static int env = [] { const char* e = std::getenv("RR_CUDA_PACKET_CTAS_PER_SM"); return e ? std::atoi(e) : 0; }();
-    return std::min(env > 0 ? env : 7, 16);
+    return std::min(env > 0 ? env : 8, 16);
 }
 
 void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
@@ -689,6 +740,23 @@ void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
     static const int force_generic = [] { const char* e = std::getenv("RR_CUDA_TRACE_GENERIC"); return e ? std::atoi(e) : 0; }();
     static const int no_packets    = [] { const char* e = std::getenv("RR_CUDA_TRACE_PACKETS"); return e && std::atoi(e) == 0 ? 1 : 0; }();
     P.force_generic = force_generic;
+    // Experiment switch (north_star: "L2-persistence staging of top BVH levels"): RR_CUDA_L2_WINDOW_MB=<n> marks the first n MB
+    // of the traced buffer as persisting in L2 for the kernels of this stream.  Measured on C2 / C3 / C4
+    // (profiles/round2_summary.md): no gain -- the 33.6 MB Sponza BVH already stays resident in the 126 MB L2 because rays and
+    // hits stream through with evict-first loads / stores -- so it is off by default.
+    static const int l2_window_mb = [] { const char* e = std::getenv("RR_CUDA_L2_WINDOW_MB"); return e ? std::atoi(e) : 0; }();
+    if (l2_window_mb > 0)
+    {
+        static std::once_flag limit_once[kMaxDevices];
+        std::call_once(limit_once[dev.device % kMaxDevices], [&] { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)l2_window_mb << 20); });
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr  = const_cast<void*>(a.scene);
+        attr.accessPolicyWindow.num_bytes = (size_t)l2_window_mb << 20;
+        attr.accessPolicyWindow.hitRatio  = 1.0f;
+        attr.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+        RR_CUDA_CHECK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
     RR_CUDA_CHECK(cudaMemsetAsync(a.scratch, 0, 8 * sizeof(uint32_t), s));
     const bool any = a.query == RR_INTERSECT_QUERY_ANY, full = a.output == RR_INTERSECT_QUERY_OUTPUT_FULL_HIT;
     // One-level kernels (they return at once when the buffer turns out to be a scene) ...
@@ -699,8 +767,15 @@ void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
             Q.chunk_list = chunk_list;
             const size_t need = ((size_t)a.ray_count + 2 * kPacketThreads - 1) / (2 * kPacketThreads);
             const int    grid = (int)std::max<size_t>(1, std::min<size_t>(need, (size_t)dev.sm_count * packet_ctas_per_sm()));
-            if (full) k_trace_packet<true><<<grid, kPacketThreads, 0, s>>>(Q);
-            else      k_trace_packet<false><<<grid, kPacketThreads, 0, s>>>(Q);
+            static const int top_levels = [] { const char* e = std::getenv("RR_CUDA_PACKET_TOP_LEVELS"); return e ? std::atoi(e) : 0; }();
+            if (top_levels)
+            {   // experiment only (see k_trace_packet): root node 0 is staged with tag 0 | slot 0, i.e. cur = kTopTag
+                const size_t smem = kTopNodes * (4 * sizeof(float4) + sizeof(uint32_t));
+                if (full) k_trace_packet<true, true><<<grid, kPacketThreads, smem, s>>>(Q);
+                else      k_trace_packet<false, true><<<grid, kPacketThreads, smem, s>>>(Q);
+            }
+            else if (full) k_trace_packet<true, false><<<grid, kPacketThreads, 0, s>>>(Q);
+            else           k_trace_packet<false, false><<<grid, kPacketThreads, 0, s>>>(Q);
             *dev.launches += 1;
         }
         if (any) { if (full) launch<true, true, false>(dev, s, Q); else launch<true, false, false>(dev, s, Q); }
