@@ -319,7 +319,7 @@ def run_ours(args):
     # ---- config C3: one 16 Mi-ray batch (diffuse CLOSEST / FULL_HIT and shadow ANY / ids) sharded over the ranks, strong scaling ----
     c3 = None
     if not args.no_c3:
-        c3 = c3_strong(eng, geom, pos, idx, rank, world, timed, resubmitter)
+        c3 = c3_strong(eng, geom, pos, idx, rank, world, timed, resubmitter, args_blocks=args.c3_blocks)
 
     # ---- config C4: 1 000 instanced Sponza BLASes under a TLAS (N=1) ------------------------------------------------
     c4 = None
@@ -384,7 +384,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def c3_strong(eng, geom, pos, idx, rank, world, timed, resubmitter, count=1 << 24, steps=5):
+def c3_strong(eng, geom, pos, idx, rank, world, timed, resubmitter, count=1 << 24, steps=5, args_blocks=1):
     """BASELINE config C3: ONE batch of 16 Mi rays (shadow ANY / ids, diffuse-bounce CLOSEST / FULL_HIT) sharded contiguously over
     the ranks (sharding.shard_range), every rank's hits landing in rank 0's buffer by peer stores from the traversal kernels inside
     the timed region.  Strong scaling: total work is fixed, the time at N ranks is what a client on rank 0 waits for all hits."""
@@ -404,25 +404,37 @@ def c3_strong(eng, geom, pos, idx, rank, world, timed, resubmitter, count=1 << 2
         if world > 1:
             dist.broadcast(t, src=0)
         d_rays[name] = t
-    b, e = sharding.shard_range(count, rank, world)
-    scratch = torch.empty(max(ctx.trace_requirements(e - b), 256), dtype=torch.uint8, device=dev)
+    # One contiguous slice per rank by default.  --c3-blocks k cuts the batch into world x k blocks dealt round-robin (rank r traces
+    # blocks r, r + world, ...; one rrCmdIntersect each in one command stream) to even out the cost of image regions -- measured at
+    # N = 8: 1.56 ms (k = 1), 2.49 ms (k = 4), 3.76 ms (k = 8) for the diffuse batch: every extra call pays the tail of a persistent
+    # grid that 512 Ki incoherent rays under-fill (3 chunks per warp), far more than the imbalance it removes.
+    blocks_per_rank = 1 if world == 1 else args_blocks
+    nblocks = world * blocks_per_rank
+    spans = [sharding.shard_range(count, rank + world * k, nblocks) for k in range(blocks_per_rank)]
+    biggest = max(e - b for b, e in spans)
+    scratch = torch.empty(max(ctx.trace_requirements(biggest), 256), dtype=torch.uint8, device=dev)
     p_scratch = ctx.tensor_ptr(scratch)
+    out["blocks_per_rank"] = blocks_per_rank
     for name, query, output, item in (("diffuse", api.RR_INTERSECT_QUERY_CLOSEST, api.RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, 16),
                                       ("shadow", api.RR_INTERSECT_QUERY_ANY, api.RR_INTERSECT_QUERY_OUTPUT_INSTANCE_ID, 4)):
-        p_rays = ctx.tensor_ptr(d_rays[name], 32 * b)
         peer, local = None, None
         if world > 1:
             peer = sharding.PeerHitBuffer(ctx, item * count, root=0)
-            p_hits = peer.ptr(item * b)
         else:
             local = torch.empty(item * count, dtype=torch.uint8, device=dev)
-            p_hits = ctx.tensor_ptr(local)
-        go = resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, query, p_rays, e - b, None, output, p_hits, p_scratch, s))
+
+        def record(s):
+            for b, e in spans:
+                if e > b:
+                    p_rays = ctx.tensor_ptr(d_rays[name], 32 * b)
+                    p_hits = peer.ptr(item * b) if peer is not None else ctx.tensor_ptr(local, item * b)
+                    ctx.cmd_intersect(geom.p_nodes, query, p_rays, e - b, None, output, p_hits, p_scratch, s)
+        go = resubmitter(record)
         ms = timed(go, steps, 2) / steps
         out[name + "_ms"] = round(ms, 4)
         out[name + "_mrays_per_s"] = round(count / ms / 1e3, 1)
         if world > 1:
-            out[name + "_nvlink_bytes_into_rank0"] = item * (count - (sharding.shard_range(count, 0, world)[1]))
+            out[name + "_nvlink_bytes_into_rank0"] = item * (count - sum(e - b for b, e in [sharding.shard_range(count, world * k, nblocks) for k in range(blocks_per_rank)]))
             if dist.get_rank() == 0:
                 got = peer.read(np.uint8)
                 sel = np.arange(0, count, 4099)
@@ -615,6 +627,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the 50 M-triangle build / refit leg (N=1 only; ~2 s, 9 GB)")
     ap.add_argument("--no-c3", action="store_true", help="skip the 16 Mi-ray shadow / diffuse strong-scaling leg")
+    ap.add_argument("--c3-blocks", type=int, default=1, help="blocks per rank of the block-cyclic C3 shards (N>1)")
     ap.add_argument("--no-c4", action="store_true", help="skip the 1 000-instance two-level leg (N=1 only)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="slices of the host batch pipelined through H2D / trace / D2H")
     args = ap.parse_args()

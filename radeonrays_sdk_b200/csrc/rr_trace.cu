@@ -491,6 +491,7 @@ __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stac
     uint32_t sp  = stack_lo;                                   // shared-memory byte address of the next free entry
     const uint32_t stack_hi = stack_lo + kPacketStack * 4;
     uint32_t cur = kTop ? kTopTag : 0u;  // the root (slot 0 of the staged top when kTop)
+    const bool lane0 = (threadIdx.x & 31) == 0;
     while (true)
     {
         float4 q0, q1, q2, q3;
@@ -519,8 +520,13 @@ __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stac
             if (any0 && any1)
             {   // defer the other child: one predicated store each instead of a select (the kernel is bound by the ALU pipe)
                 if (sp >= stack_hi) return false;
-                if (take1) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(wbits(q0)) : "memory");
-                else       asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(wbits(q1)) : "memory");
+                __syncwarp();  // every lane's earlier pop of this slot has completed
+                if (lane0)
+                {   // one lane writes the warp's stack; the barrier below orders the store before any lane's later pop
+                    if (take1) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(wbits(q0)) : "memory");
+                    else       asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(wbits(q1)) : "memory");
+                }
+                __syncwarp();
                 sp += 4;
             }
             if (any0 || any1)
