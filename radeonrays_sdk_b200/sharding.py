@@ -98,3 +98,41 @@ class PeerHitBuffer:
         if self.base is not None:
             self.ctx.release_ptr(self.base)
             self.base = None
+
+
+def build_scene_sharded(engine, meshes, instance_mesh, transforms, build_flags=0):
+    """Multi-mesh scene on N ranks ("BLAS i on GPU i mod G, then all-gather of BLAS bytes and TLAS build
+    everywhere"): rank r builds the geometries i with i % world == r through rrCmdBuildGeometry, every rank then receives the bytes
+    of every geometry from its builder (a BLAS holds indices, not pointers, so the bytes are valid anywhere), and builds the
+    scene over its local copies with rrCmdBuildScene (a TLAS build is a few microseconds; a scene built elsewhere would instead be
+    broadcast and re-pointed with rrCudaCmdRebindSceneGeometry).  `meshes`: list of (positions, indices) present on every rank.
+    Returns (geometries, scene) as radeonrays_sdk_b200.host objects; with one rank it is a plain local build."""
+    from .host import Geometry, _dev_bytes
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    ctx = engine.ctx
+    geoms = []
+    for i, (pos, idx) in enumerate(meshes):
+        if i % world == rank:
+            g = engine.build_geometry(pos, idx, build_flags=build_flags)
+        else:   # a receive-only geometry: the result buffer of the right size, no build
+            g = Geometry()
+            g.engine, g.triangle_count = engine, int(idx.shape[0])
+            probe = ctx.geometry_input(ctx.device_ptr(256), int(pos.shape[0]), 12, ctx.device_ptr(256), int(idx.shape[0]))
+            from . import api
+            req = ctx.geometry_requirements(probe, api.RRBuildOptions(build_flags, None))
+            g.d_nodes = _dev_bytes(req.result_buffer_size, engine.device)
+            g.p_nodes = ctx.tensor_ptr(g.d_nodes)
+        geoms.append(g)
+    torch.cuda.synchronize(engine.device)
+    if world > 1:
+        on_gpu = dist.get_backend() == "nccl"
+        for i, g in enumerate(geoms):
+            if on_gpu:
+                dist.broadcast(g.d_nodes, src=i % world)
+            else:   # gloo (tests): stage through the host
+                host = g.d_nodes.cpu()
+                dist.broadcast(host, src=i % world)
+                g.d_nodes.copy_(host)
+    scene = engine.build_scene(geoms, list(instance_mesh), transforms)
+    return geoms, scene
