@@ -433,6 +433,19 @@ def c3_strong(eng, geom, pos, idx, rank, world, timed, resubmitter, count=1 << 2
         ms = timed(go, steps, 2) / steps
         out[name + "_ms"] = round(ms, 4)
         out[name + "_mrays_per_s"] = round(count / ms / 1e3, 1)
+        if world == 1 and name == "diffuse":
+            # the same batch with on-device ray binning (RR_CUDA_OPTION_SORT_RAYS: key pass + radix sort inside the timed call,
+            # bit-identical hits in the client's order; tests/test_gpu_trace.py::test_ray_binning_option_is_bit_identical)
+            ctx.set_option(api.RR_CUDA_OPTION_SORT_RAYS, 1)
+            big = torch.empty(ctx.trace_requirements(count), dtype=torch.uint8, device=dev)
+            p_big = ctx.tensor_ptr(big)
+            p_r, p_h = ctx.tensor_ptr(d_rays[name]), ctx.tensor_ptr(local)
+            go2 = resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, query, p_r, count, None, output, p_h, p_big, s))
+            ctx.set_option(api.RR_CUDA_OPTION_SORT_RAYS, 0)
+            ms2 = timed(go2, steps, 2) / steps
+            out["diffuse_binned_ms"] = round(ms2, 4)
+            out["diffuse_binned_mrays_per_s"] = round(count / ms2 / 1e3, 1)
+            del big
         if world > 1:
             out[name + "_nvlink_bytes_into_rank0"] = item * (count - sum(e - b for b, e in [sharding.shard_range(count, world * k, nblocks) for k in range(blocks_per_rank)]))
             if dist.get_rank() == 0:

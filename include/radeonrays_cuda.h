@@ -50,6 +50,11 @@ typedef enum
 {
     RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND   = 1,
     RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK = 2,
+    /* 1 = every rrCmdIntersect recorded afterwards first bins its rays on the device (direction octant, origin cell, coarse
+     * direction: one key pass + a 3-pass radix sort) and traces them in that order; hits are bit-identical and stay in the
+     * client's order.  For INCOHERENT batches (diffuse bounces); coherent batches are faster without.  Set it before
+     * rrGetTraceMemoryRequirements: the scratch buffer grows by ~18 bytes per ray. */
+    RR_CUDA_OPTION_SORT_RAYS                      = 4,
     /* test hook: caps the hand-over lists of the staged refit (0 = library default) so that tests can drive them into overflow */
     RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY      = 3
 } RRCudaOption;

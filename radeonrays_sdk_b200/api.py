@@ -29,6 +29,7 @@ RR_INTERSECT_QUERY_OUTPUT_FULL_HIT, RR_INTERSECT_QUERY_OUTPUT_INSTANCE_ID = 0, 1
 RR_INVALID_VALUE = 0xFFFFFFFF
 RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK = 1, 2
 RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY = 3
+RR_CUDA_OPTION_SORT_RAYS = 4
 
 _vp = C.c_void_p
 

@@ -628,6 +628,7 @@ RRError rrCudaSetOption(RRContext context, RRCudaOption option, int value)
     {
     case RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND: C(context)->first_found_tie_rule = value != 0; return RR_SUCCESS;
     case RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK: C(context)->reference_corner_quirk = value != 0; return RR_SUCCESS;
+    case RR_CUDA_OPTION_SORT_RAYS: C(context)->dev.sort_rays = value != 0; return RR_SUCCESS;
     case RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY: C(context)->dev.refit_list_capacity = value > 0 ? (uint32_t)value : 0u; return RR_SUCCESS;
     default: return RR_ERROR_INVALID_PARAMETER;
     }

@@ -98,6 +98,7 @@ struct DeviceInfo
     int      sm_count    = 148;
     size_t   l2_bytes    = 0;
     uint64_t* launches   = nullptr;  // per-context launch counter (host side)
+    bool      sort_rays  = false;    // RR_CUDA_OPTION_SORT_RAYS: bin the rays of every rrCmdIntersect on the device before tracing
     uint32_t  refit_list_capacity = 0;  // test hook (RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY): 0 = sized by the library
     uint32_t* error_word = nullptr;  // device-visible (host-mapped) word the kernels OR error bits into; checked by rrWaitEvent
 };
@@ -115,8 +116,9 @@ void sort_reset(const DeviceInfo& dev, cudaStream_t s, const SortLayout& L, void
 void sort_histogram(const DeviceInfo& dev, cudaStream_t s, const SortLayout& L, void* scratch, const uint32_t* keys);
 // 4 onesweep passes. keys_in is clobbered only if it aliases nothing else; result lands in keys_out/vals_out.
 // vals_in == nullptr means "values are 0..n-1" (generated on the fly in the first pass).
+// `passes` least-significant 8-bit digits are sorted (4 = full 32-bit keys).
 void sort_pairs(const DeviceInfo& dev, cudaStream_t s, const SortLayout& L, void* scratch, uint32_t* keys_in,
-                const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out);
+                const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, int passes = 4);
 uint32_t* sort_hist_ptr(const SortLayout& L, void* scratch);
 
 // ---- build (rr_build.cu) ------------------------------------------------------------------------------

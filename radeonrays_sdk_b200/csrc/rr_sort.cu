@@ -278,8 +278,9 @@ void sort_histogram(const DeviceInfo& dev, cudaStream_t s, const SortLayout& L, 
 }
 
 void sort_pairs(const DeviceInfo& dev, cudaStream_t s, const SortLayout& L, void* scratch, uint32_t* keys_in, const uint32_t* vals_in,
-                uint32_t* keys_out, uint32_t* vals_out)
+                uint32_t* keys_out, uint32_t* vals_out, int passes)
 {
+    passes = std::max(1, std::min(passes, kPasses));
     if (L.n == 0) return;
     static std::once_flag attr_once[kMaxDevices];  // once per device, thread-safe (contexts may live on different threads)
     std::call_once(attr_once[dev.device % kMaxDevices], [] {
@@ -294,10 +295,10 @@ void sort_pairs(const DeviceInfo& dev, cudaStream_t s, const SortLayout& L, void
     uint32_t* tmp_vals = reinterpret_cast<uint32_t*>(sc + L.tmp_vals_off);
     const uint32_t* kin = keys_in;
     const uint32_t* vin = vals_in;
-    for (int p = 0; p < kPasses; ++p)
-    {
-        uint32_t* kout = (p & 1) ? keys_out : tmp_keys;
-        uint32_t* vout = (p & 1) ? vals_out : tmp_vals;
+    for (int p = 0; p < passes; ++p)
+    {   // ping-pong so that the last pass lands in keys_out / vals_out
+        uint32_t* kout = ((passes - 1 - p) & 1) ? tmp_keys : keys_out;
+        uint32_t* vout = ((passes - 1 - p) & 1) ? tmp_vals : vals_out;
         uint32_t* st   = status + (size_t)p * L.tiles * kRadix;
         if (p == 0 && vin == nullptr)
             k_onesweep_pass<true><<<L.tiles, kSortThreads, kSortSmemBytes, s>>>(kin, nullptr, kout, vout, L.n, p * kRadixBits,

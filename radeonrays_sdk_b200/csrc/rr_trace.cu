@@ -219,6 +219,7 @@ struct TraceParams
     uint32_t*             packet_ticket;  // word 3: packet counter of k_trace_packet
     uint32_t*             chunk_count;    // word 4: 32-ray chunks k_trace_packet handed to the per-ray kernel
     uint32_t*             chunk_list;     // [ceil(ray_count / 32)] their chunk indices; nullptr: k_trace walks all chunks itself
+    const uint32_t*       perm;           // RR_CUDA_OPTION_SORT_RAYS: position -> ray index in binned order; nullptr: client order
     int                   first_found;
     int                   force_generic;
     uint32_t*             error;          // DeviceInfo::error_word
@@ -399,9 +400,12 @@ __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(Tra
         }
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if ((uint64_t)chunk * 32 >= count) break;
-        const uint32_t gidx  = chunk * 32 + lane;
-        const bool     valid = gidx < count;
-        const uint32_t ridx  = valid ? gidx : count - 1;  // tail lanes shadow the last ray and write nothing
+        uint32_t gidx  = chunk * 32 + lane;
+        const bool valid = gidx < count;
+        // binned order: the warp takes 32 neighbours of the sorted sequence; everything below (ray load, hit store, overflow
+        // list) uses the ray's own index, so the client sees its own order (rays past a device-side count sort last)
+        if (P.perm) gidx = __ldg(P.perm + (valid ? gidx : count - 1));
+        const uint32_t ridx  = valid ? gidx : (P.perm ? gidx : count - 1);  // tail lanes shadow a valid ray and write nothing
         // rays are read once: streaming loads (evict-first) keep them from displacing BVH nodes in L1 / L2
         const float4 r0 = __ldcs(P.rays + 2 * (size_t)ridx), r1 = __ldcs(P.rays + 2 * (size_t)ridx + 1);
         RayState ray;
@@ -657,6 +661,91 @@ __global__ void __launch_bounds__(kPacketThreads, 8) k_trace_packet(TraceParams 
     }
 }
 
+// ---- on-device ray binning (RR_CUDA_OPTION_SORT_RAYS) ------------------------------------------------------------------------------
+// Incoherent batches (diffuse bounces) make the 32 rays of a warp walk 32 different paths: every node fetch is a divergent load and
+// the warp runs as long as its slowest ray.  With the option set, every rrCmdIntersect first computes a 30-bit key per ray --
+// direction octant (3 bits) | 6-bit-per-axis Morton cell of the origin inside the root box (18) | 3 bits per axis of the normalised
+// |direction| (9) -- sorts (key, ray index) with the builder's onesweep sort, and k_trace then takes its 32-ray chunks from the
+// sorted sequence.  (RR_CUDA_SORT_KEY_MODE=0: 24-bit keys, 5-bit cells, 2-bit directions, three passes: 2 132 against 2 184 Mrays/s
+// on the C3 diffuse batch; =2: direction before cell: 2 131.)  A ray is still traced by one lane with the reference's visit order and writes its hit at its own
+// index, so results are bit-identical and in the client's order.  No reference counterpart (the reference traces in buffer order).
+__device__ __forceinline__ uint32_t spread5(uint32_t v)
+{   // 5 bits -> every third bit
+    v = (v | (v << 8)) & 0x0000100Fu;
+    v = (v | (v << 4)) & 0x000010C3u;
+    v = (v | (v << 2)) & 0x00001249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t spread6(uint32_t v)
+{   // 6 bits -> every third bit
+    v = (v | (v << 8)) & 0x0000300Fu;
+    v = (v | (v << 4)) & 0x000030C3u;
+    v = (v | (v << 2)) & 0x00009249u;
+    return v;
+}
+__global__ void __launch_bounds__(256) k_ray_keys(const void* scene, const float4* __restrict__ rays, uint32_t ray_count,
+                                                   const uint32_t* __restrict__ indirect, uint32_t* __restrict__ keys, int mode)
+{
+    // root box: node 0 of the geometry, or of the TLAS when the buffer is a scene
+    const uint4 m     = __ldg(reinterpret_cast<const uint4*>(scene));
+    const char* base  = reinterpret_cast<const char*>(scene);
+    if (m.x == kSceneMagic0 && m.y == kSceneMagic1 && m.z == kSceneMagic2 && m.w == kSceneMagic3)
+        base += reinterpret_cast<const SceneHeader*>(scene)->nodes_off;
+    const float4* root = reinterpret_cast<const float4*>(base);
+    const float4  q0 = __ldg(root), q1 = __ldg(root + 1), q2 = __ldg(root + 2), q3 = __ldg(root + 3);
+    float lo[3], hi[3];
+    if (wbits(q0) != kInvalid)
+    {
+        lo[0] = fminf(q0.x, q2.x); lo[1] = fminf(q0.y, q2.y); lo[2] = fminf(q0.z, q2.z);
+        hi[0] = fmaxf(q1.x, q3.x); hi[1] = fmaxf(q1.y, q3.y); hi[2] = fmaxf(q1.z, q3.z);
+    }
+    else
+    {   // single leaf: its vertices (or its box, for a one-instance TLAS)
+        lo[0] = fminf(q0.x, fminf(q1.x, q2.x)); lo[1] = fminf(q0.y, fminf(q1.y, q2.y)); lo[2] = fminf(q0.z, fminf(q1.z, q2.z));
+        hi[0] = fmaxf(q0.x, fmaxf(q1.x, q2.x)); hi[1] = fmaxf(q0.y, fmaxf(q1.y, q2.y)); hi[2] = fmaxf(q0.z, fmaxf(q1.z, q2.z));
+    }
+    uint32_t count = ray_count;
+    if (indirect) count = min(count, __ldg(indirect));
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ray_count; i += gridDim.x * blockDim.x)
+    {
+        uint32_t key = mode ? 0x3FFFFFFFu : 0x00FFFFFFu;  // rays past the device-side count sort last (ties keep index order: the sort is stable)
+        if (i < count)
+        {
+            const float4 r0 = __ldg(rays + 2 * (size_t)i), r1 = __ldg(rays + 2 * (size_t)i + 1);
+            const float  o[3] = {r0.x, r0.y, r0.z}, d[3] = {r1.x, r1.y, r1.z};
+            const float  len = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            uint32_t cell[3], dq = 0, oct = 0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+            {
+                const float ext = hi[a] - lo[a];
+                const float t   = ext > 0.0f ? (o[a] - lo[a]) / ext * 32.0f : 0.0f;
+                cell[a] = (uint32_t)fminf(fmaxf(t, 0.0f), 31.0f);                       // (NaN -> 0)
+                const float q = len > 0.0f ? fabsf(d[a]) / len * 4.0f : 0.0f;
+                dq |= (uint32_t)fminf(fmaxf(q, 0.0f), 3.0f) << (2 * a);
+                oct |= (__float_as_uint(d[a]) >> 31) << a;
+            }
+            key = (oct << 21) | (((spread5(cell[0]) << 2) | (spread5(cell[1]) << 1) | spread5(cell[2])) << 6) | dq;
+            if (mode)
+            {   // experiment: 6-bit cells, 3 bits per axis of direction: 30-bit keys, four passes
+                uint32_t c6[3], d3 = 0;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                {
+                    const float ext = hi[a] - lo[a];
+                    const float t   = ext > 0.0f ? (o[a] - lo[a]) / ext * 64.0f : 0.0f;
+                    c6[a] = (uint32_t)fminf(fmaxf(t, 0.0f), 63.0f);
+                    const float q = len > 0.0f ? fabsf(d[a]) / len * 8.0f : 0.0f;
+                    d3 |= (uint32_t)fminf(fmaxf(q, 0.0f), 7.0f) << (3 * a);
+                }
+                const uint32_t mc = (spread6(c6[0]) << 2) | (spread6(c6[1]) << 1) | spread6(c6[2]);
+                key = mode == 1 ? (oct << 27) | (mc << 9) | d3 : (oct << 27) | (d3 << 18) | mc;
+            }
+        }
+        keys[i] = key;
+    }
+}
+
 // Second launch of every intersect: traces the (normally zero) rays whose deferred-node stack outgrew shared memory,
 // with the generic loop and a global-memory stack.  Exits at once when the list is empty.
 template <bool kAny, bool kFullHit, bool kTwoLevel>
@@ -716,10 +805,16 @@ void launch(const DeviceInfo& dev, cudaStream_t s, const TraceParams& P)
 constexpr size_t kScratchHeader = 256;
 static size_t overflow_list_bytes(uint32_t ray_count) { return align_up(sizeof(uint32_t) * (size_t)ray_count, 256); }
 static size_t chunk_list_bytes(uint32_t ray_count) { return align_up(sizeof(uint32_t) * (((size_t)ray_count + 31) / 32 + 1), 256); }
+static size_t deep_arena_bytes(const DeviceInfo& dev, uint32_t ray_count)
+{
+    return align_up((size_t)trace_grid(dev, ray_count, kDeepCtasPerSm) * kTraceThreads * kDeepStack * sizeof(uint32_t), 256);
+}
+// With RR_CUDA_OPTION_SORT_RAYS: + [keys 4 B | permutation 4 B per ray | scratch of the radix sort]
+static size_t ray_sort_bytes(uint32_t ray_count) { return 2 * align_up(sizeof(uint32_t) * (size_t)ray_count, 256) + sort_layout(ray_count).total; }
 size_t trace_scratch_size(const DeviceInfo& dev, uint32_t ray_count)
 {
-    return kScratchHeader + overflow_list_bytes(ray_count) + chunk_list_bytes(ray_count) +
-           (size_t)trace_grid(dev, ray_count, kDeepCtasPerSm) * kTraceThreads * kDeepStack * sizeof(uint32_t);
+    return kScratchHeader + overflow_list_bytes(ray_count) + chunk_list_bytes(ray_count) + deep_arena_bytes(dev, ray_count) +
+           (dev.sort_rays ? ray_sort_bytes(ray_count) : 0);
 }
 
 // Resident CTAs per SM of the packet kernel (RR_CUDA_PACKET_CTAS_PER_SM overrides it for tuning).
@@ -742,6 +837,7 @@ void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
     uint32_t* chunk_list = P.overflow_list + overflow_list_bytes(a.ray_count) / sizeof(uint32_t);
     P.arena = chunk_list + chunk_list_bytes(a.ray_count) / sizeof(uint32_t);
     P.chunk_list = nullptr;
+    P.perm = nullptr;
     P.error = dev.error_word;
     static const int force_generic = [] { const char* e = std::getenv("RR_CUDA_TRACE_GENERIC"); return e ? std::atoi(e) : 0; }();
     static const int no_packets    = [] { const char* e = std::getenv("RR_CUDA_TRACE_PACKETS"); return e && std::atoi(e) == 0 ? 1 : 0; }();
@@ -765,10 +861,28 @@ void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
     }
     RR_CUDA_CHECK(cudaMemsetAsync(a.scratch, 0, 8 * sizeof(uint32_t), s));
     const bool any = a.query == RR_INTERSECT_QUERY_ANY, full = a.output == RR_INTERSECT_QUERY_OUTPUT_FULL_HIT;
+    if (dev.sort_rays)
+    {   // bin the rays: keys -> 3-pass onesweep over (key, index) -> k_trace walks the permutation (no packets: binned neighbours
+        // share an octant and a cell, not a path)
+        char*            sb   = reinterpret_cast<char*>(P.arena) + deep_arena_bytes(dev, a.ray_count);
+        uint32_t*        keys = reinterpret_cast<uint32_t*>(sb);
+        uint32_t*        perm = reinterpret_cast<uint32_t*>(sb + align_up(sizeof(uint32_t) * (size_t)a.ray_count, 256));
+        void*            ss   = sb + 2 * align_up(sizeof(uint32_t) * (size_t)a.ray_count, 256);
+        const SortLayout SL   = sort_layout(a.ray_count);
+        const int        grid = (int)std::min<size_t>(((size_t)a.ray_count + 255) / 256, (size_t)dev.sm_count * 8);
+        static const int key_mode = [] { const char* e = std::getenv("RR_CUDA_SORT_KEY_MODE"); return e ? std::atoi(e) : 1; }();
+        k_ray_keys<<<grid, 256, 0, s>>>(a.scene, P.rays, a.ray_count, a.indirect_count, keys, key_mode);
+        *dev.launches += 1;
+        sort_reset(dev, s, SL, ss);
+        sort_histogram(dev, s, SL, ss, keys);
+        // (the sorted keys are of no use afterwards: they land in the overflow list, which only k_trace writes, later)
+        sort_pairs(dev, s, SL, ss, keys, nullptr, P.overflow_list, perm, key_mode ? 4 : 3);
+        P.perm = perm;
+    }
     // One-level kernels (they return at once when the buffer turns out to be a scene) ...
     {
         TraceParams Q = P;
-        if (!any && !a.first_found_tie_rule && !no_packets)
+        if (!any && !a.first_found_tie_rule && !no_packets && !dev.sort_rays)
         {   // closest hit under the (t, prim) rule: coherent 64-ray packets first, whatever they decline goes to k_trace in list mode
             Q.chunk_list = chunk_list;
             const size_t need = ((size_t)a.ray_count + 2 * kPacketThreads - 1) / (2 * kPacketThreads);

@@ -209,3 +209,42 @@ def test_resubmitted_command_stream_is_replayed_as_a_graph(engine, sponza):
         ctx.release_event(e)
         assert int((ids == -2).sum().item()) == 0
     ctx.release_command_stream(cs)
+
+
+def test_ray_binning_option_is_bit_identical(engine, sponza, cornell):
+    """RR_CUDA_OPTION_SORT_RAYS: rays binned on the device (octant | origin cell | coarse direction, 3-pass radix sort) and traced in
+    that order; every mode must return exactly what the unsorted trace returns, in the client's order -- one level, two level,
+    ragged counts, a device-side ray count, misses left untouched."""
+    pos, idx, _ = sponza
+    g = engine.build_geometry(pos, idx, build_flags=0)
+    prim = W.sponza_primary_rays(256, 256)
+    hits = engine.intersect(g, prim)
+    diffuse = W.diffuse_rays(pos, idx, prim, hits, count=150_001)
+    rng = np.random.default_rng(9)
+    init = np.zeros(diffuse.shape[0], W.HIT_DTYPE)
+    init["uv"] = rng.random((diffuse.shape[0], 2), dtype=np.float32)
+    init["prim_id"], init["inst_id"] = 4242, 77
+    cpos, cidx, _ = cornell
+    cg = engine.build_geometry(cpos, cidx)
+    xf = W.grid_instances(n_side=3, spacing=3.0, degrees_per_instance=9.0)
+    sc = engine.build_scene([cg], [0] * xf.shape[0], xf)
+    rnd = W.random_rays(70_003, (-2, -2, -2), (9, 9, 9), seed=5)
+    cases = [(g, diffuse, CLOSEST, FULL, init, None), (g, diffuse, ANY, IDS, None, None), (g, diffuse, CLOSEST, IDS, None, 100_000),
+             (sc, rnd, CLOSEST, FULL, None, None), (sc, rnd, ANY, FULL, None, 12_345), (g, diffuse[:31], CLOSEST, FULL, None, None)]
+    engine.ctx.set_option(api.RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, 1)     # per-ray kernel in both runs: bit for bit
+    try:
+        plain = [engine.intersect(t, r, q, o, init_hits=(i[: r.shape[0]] if i is not None else None), indirect_count=c) for t, r, q, o, i, c in cases]
+        engine.ctx.set_option(api.RR_CUDA_OPTION_SORT_RAYS, 1)
+        binned = [engine.intersect(t, r, q, o, init_hits=(i[: r.shape[0]] if i is not None else None), indirect_count=c) for t, r, q, o, i, c in cases]
+    finally:
+        engine.ctx.set_option(api.RR_CUDA_OPTION_SORT_RAYS, 0)
+        engine.ctx.set_option(api.RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, 0)
+    for k, (a, b) in enumerate(zip(plain, binned)):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"case {k}: binned trace differs"
+    # default tie rule + binning (per-ray kernel) against the oracle
+    engine.ctx.set_option(api.RR_CUDA_OPTION_SORT_RAYS, 1)
+    try:
+        got = engine.intersect(g, diffuse)
+    finally:
+        engine.ctx.set_option(api.RR_CUDA_OPTION_SORT_RAYS, 0)
+    assert_hits_equal(got, O.trace(g.nodes(), diffuse), what="binned diffuse", mesh=(pos, idx), rays=diffuse)
