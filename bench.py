@@ -523,8 +523,17 @@ def build_c5(eng, nx=5000, nz=5000, reps=5):
     pos2, _ = heightfield_device(nx, nz, 1.0, dev)
     g.d_vertices.copy_(pos2.view(torch.uint8).reshape(-1))
     ms_refit = timed(api.RR_BUILD_OPERATION_UPDATE)
+    # the same mesh with 63-bit Morton codes (RR_CUDA_OPTION_MORTON_BITS = 63: two 4-pass sorts instead of one)
+    ctx.set_option(api.RR_CUDA_OPTION_MORTON_BITS, 63)
+    req63 = ctx.geometry_requirements(g.input, g.options)
+    g.d_temp = None
+    torch.cuda.empty_cache()
+    g.d_temp = _dev_bytes(req63.temporary_build_buffer_size, dev)
+    g.p_temp = ctx.tensor_ptr(g.d_temp)
+    ms_build63 = timed(api.RR_BUILD_OPERATION_BUILD)
+    ctx.set_option(api.RR_CUDA_OPTION_MORTON_BITS, 30)
     peak, _ = measured_peak_gbs()
-    out = {"workload": f"C5: height field {nx}x{nz}, {n} triangles", "build_ms": round(ms_build, 4),
+    out = {"workload": f"C5: height field {nx}x{nz}, {n} triangles", "build_ms": round(ms_build, 4), "build_morton63_ms": round(ms_build63, 4),
            "build_mtris_per_s": round(n / ms_build / 1e3, 1), "build_gbs": round(BUILD_BYTES_PER_TRI * n / ms_build / 1e6, 1),
            "build_roofline_frac": round(BUILD_BYTES_PER_TRI * n / ms_build / 1e6 / peak, 4), "refit_ms": round(ms_refit, 4),
            "refit_mtris_per_s": round(n / ms_refit / 1e3, 1), "refit_gbs": round(REFIT_BYTES_PER_TRI * n / ms_refit / 1e6, 1),

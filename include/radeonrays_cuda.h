@@ -55,6 +55,11 @@ typedef enum
      * client's order.  For INCOHERENT batches (diffuse bounces); coherent batches are faster without.  Set it before
      * rrGetTraceMemoryRequirements: the scratch buffer grows by ~18 bytes per ray. */
     RR_CUDA_OPTION_SORT_RAYS                      = 4,
+    /* 30 (default, the reference's codes) or 63: geometry builds recorded afterwards sort the triangles by 63-bit Morton codes
+     * (21 bits per axis) -- far fewer equal codes on large or unevenly tessellated meshes.  An extension: the reference only keeps
+     * a compiled-out 64-bit delta() (dx/kernels/build_hlbvh_fallback.hlsl:16,95-108); defined by oracle/rr_oracle.c
+     * rro_build_blas63.  Set it before rrGetGeometryBuildMemoryRequirements (the temporary build buffer grows). */
+    RR_CUDA_OPTION_MORTON_BITS                    = 5,
     /* test hook: caps the hand-over lists of the staged refit (0 = library default) so that tests can drive them into overflow */
     RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY      = 3
 } RRCudaOption;

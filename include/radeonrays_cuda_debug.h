@@ -16,7 +16,8 @@ extern "C" {
 
 /* Byte offsets, inside the temporary build buffer of a geometry with `triangle_count` triangles, of the
  * intermediate arrays the build leaves behind: scene AABB (uint[8], ordered encoding, reference
- * lbvh_init_mesh.comp:61-77), unsorted Morton codes, sorted codes (u32[N] each).  The sorted primitive refs (u32[N]) are kept in
+ * lbvh_init_mesh.comp:61-77), unsorted Morton codes, sorted codes (u32[N] each; with RR_CUDA_OPTION_MORTON_BITS = 63 the sorted codes
+ * are u64[N] and morton_codes_offset holds their unsorted low words).  The sorted primitive refs (u32[N]) are kept in
  * the GEOMETRY buffer, after the node array, where RR_BUILD_OPERATION_UPDATE reads them: sorted_refs_offset is an offset
  * into the geometry buffer. */
 typedef struct

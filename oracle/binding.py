@@ -92,6 +92,17 @@ def build_blas(verts, idx, restructure=False):
     return nodes, sc, sr
 
 
+def build_blas63(verts, idx, restructure=False):
+    """63-bit Morton extension -> (nodes[2N-1], sorted_codes u64[N], sorted_refs[N])"""
+    verts, idx = _f32(verts), _u32(idx)
+    n = idx.shape[0]
+    nodes = np.zeros(2 * n - 1, NODE_DTYPE)
+    sc, sr = np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+    lib().rro_build_blas63(_p(verts), C.c_uint32(verts.shape[1]), _p(idx), C.c_uint32(n), C.c_int(int(restructure)),
+                           _p(nodes), _p(sc), _p(sr))
+    return nodes, sc, sr
+
+
 def refit(nodes, verts, idx):
     verts, idx = _f32(verts), _u32(idx)
     nodes = nodes.copy()

@@ -189,14 +189,23 @@ static inline int ref_clz(uint32_t v) /* :78-81  32 - findMSB(v); findMSB(0) == 
         if (v >> b) { msb = b; break; }
     return 32 - msb;
 }
-static inline int common_prefix(const uint32_t* codes, int64_t n, int64_t i1, int64_t i2) /* :85-103 */
+/* `codes` is uint32_t[] (the reference's 30-bit codes) or, for the 63-bit extension, uint64_t[] -- then the prefix is the one
+ * dx/kernels/build_hlbvh_fallback.hlsl:95-108 sketches behind its compiled-out !USE_30BIT_MORTON_CODE branch:
+ * clz64(l ^ r), ties broken by 64 + clz64 of the indices.  Selected by the sign of n_wide (see emit_hierarchy). */
+typedef struct { const void* p; int wide; } code_array;
+static inline int common_prefix(code_array codes, int64_t n, int64_t i1, int64_t i2) /* :85-103 */
 {
     int64_t l = i1 < i2 ? i1 : i2, r = i1 < i2 ? i2 : i1;
     if (l < 0 || r >= n) return 0;
-    uint32_t lc = codes[l], rc = codes[r];
+    if (codes.wide)
+    {
+        uint64_t lc = ((const uint64_t*)codes.p)[l], rc = ((const uint64_t*)codes.p)[r];
+        return lc != rc ? 1 + __builtin_clzll(lc ^ rc) : 1 + 64 + __builtin_clzll((uint64_t)(l ^ r));
+    }
+    uint32_t lc = ((const uint32_t*)codes.p)[l], rc = ((const uint32_t*)codes.p)[r];
     return lc != rc ? ref_clz(lc ^ rc) : 32 + ref_clz((uint32_t)(l ^ r));
 }
-static void find_span(const uint32_t* codes, int64_t n, int64_t i, int64_t* sx, int64_t* sy) /* :105-140 */
+static void find_span(code_array codes, int64_t n, int64_t i, int64_t* sx, int64_t* sy) /* :105-140 */
 {
     int diff = common_prefix(codes, n, i, i + 1) - common_prefix(codes, n, i, i - 1);
     int64_t d = (diff > 0) - (diff < 0);
@@ -214,7 +223,7 @@ static void find_span(const uint32_t* codes, int64_t n, int64_t i, int64_t* sx, 
     *sx = lo < 0 ? 0 : lo;
     *sy = hi > n - 1 ? n - 1 : hi;
 }
-static int64_t find_split(const uint32_t* codes, int64_t n, int64_t sx, int64_t sy) /* :142-168 */
+static int64_t find_split(code_array codes, int64_t n, int64_t sx, int64_t sy) /* :142-168 */
 {
     int64_t left = sx, right = sy;
     int ident = common_prefix(codes, n, left, right);
@@ -226,7 +235,18 @@ static int64_t find_split(const uint32_t* codes, int64_t n, int64_t sx, int64_t 
     return left;
 }
 
+static void emit_hierarchy(code_array codes, const uint32_t* refs, uint32_t n, rro_node* nodes);
 void rro_emit_hierarchy(const uint32_t* codes, const uint32_t* refs, uint32_t n, rro_node* nodes) /* :170-217 */
+{
+    code_array c = {codes, 0};
+    emit_hierarchy(c, refs, n, nodes);
+}
+void rro_emit_hierarchy64(const uint64_t* codes, const uint32_t* refs, uint32_t n, rro_node* nodes)
+{
+    code_array c = {codes, 1};
+    emit_hierarchy(c, refs, n, nodes);
+}
+static void emit_hierarchy(code_array codes, const uint32_t* refs, uint32_t n, rro_node* nodes)
 {
     const uint32_t leaf0 = n - 1;
     memset(nodes, 0, sizeof(rro_node) * (size_t)(2 * (size_t)n - 1));
@@ -588,6 +608,76 @@ void rro_build_blas(const float* verts, uint32_t sf, const uint32_t* idx, uint32
     if (sorted_codes) memcpy(sorted_codes, sc, sizeof(uint32_t) * (size_t)n);
     if (sorted_refs) memcpy(sorted_refs, sr, sizeof(uint32_t) * (size_t)n);
     free(codes); free(refs); free(sc); free(sr);
+}
+
+/* ---- 63-bit Morton extension (BASELINE north_star "30/63-bit Morton codes") --------------------------------------------
+ * The reference ships 30-bit codes only; its DX fallback kernel keeps a compiled-out 64-bit branch of delta()
+ * (dx/kernels/build_hlbvh_fallback.hlsl:16,95-108) and nothing else, so there is no reference output to be exact against.
+ * Defined here as the same pipeline with 21 bits per axis: p = (centroid - sceneMin) / extent as in the 30-bit path,
+ * clamp(p * 2^21, 0, 2^21 - 1) -> uint -> 3-dilate to 63 bits, code = x << 2 | y << 1 | z; stable sort on the 64-bit key;
+ * Karras topology with the 64-bit prefix above; same fit / restructure. */
+static inline uint64_t expand_bits21(uint32_t v)
+{
+    uint64_t x = v & 0x1FFFFFu;
+    x = (x | (x << 32)) & 0x001F00000000FFFFull;
+    x = (x | (x << 16)) & 0x001F0000FF0000FFull;
+    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+void rro_morton_codes63(const float* verts, uint32_t sf, const uint32_t* idx, uint32_t n, const float smin[3],
+                        const float smax[3], uint64_t* codes)
+{
+    v3 lo = v3_ld(smin), hi = v3_ld(smax);
+    v3 ext = v3_sub(hi, lo);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        v3 v0 = v3_ld(verts + (size_t)idx[3 * (size_t)i + 0] * sf);
+        v3 v1 = v3_ld(verts + (size_t)idx[3 * (size_t)i + 1] * sf);
+        v3 v2 = v3_ld(verts + (size_t)idx[3 * (size_t)i + 2] * sf);
+        v3 bmin = v3_min(v3_min(v0, v1), v2);
+        v3 bmax = v3_max(v3_max(v0, v1), v2);
+        v3 c = v3_make(0.5f * (bmin.x + bmax.x), 0.5f * (bmin.y + bmax.y), 0.5f * (bmin.z + bmax.z));
+        v3 p = v3_sub(c, lo);
+        p    = v3_make(p.x / ext.x, p.y / ext.y, p.z / ext.z);
+        float x = rr_min(rr_max(p.x * 2097152.0f, 0.0f), 2097151.0f);
+        float y = rr_min(rr_max(p.y * 2097152.0f, 0.0f), 2097151.0f);
+        float z = rr_min(rr_max(p.z * 2097152.0f, 0.0f), 2097151.0f);
+        codes[i] = (expand_bits21((uint32_t)x) << 2) | (expand_bits21((uint32_t)y) << 1) | expand_bits21((uint32_t)z);
+    }
+}
+void rro_build_blas63(const float* verts, uint32_t sf, const uint32_t* idx, uint32_t n, int restructure, rro_node* nodes,
+                      uint64_t* sorted_codes, uint32_t* sorted_refs)
+{
+    float smin[3], smax[3];
+    uint64_t* k0 = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)n);
+    uint64_t* k1 = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)n);
+    uint32_t* v0 = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n);
+    uint32_t* v1 = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n);
+    rro_scene_aabb(verts, sf, idx, n, smin, smax);
+    rro_morton_codes63(verts, sf, idx, n, smin, smax, k0);
+    for (uint32_t i = 0; i < n; ++i) v0[i] = i;
+    for (uint32_t shift = 0; shift < 64; shift += 8) /* stable LSD counting sort */
+    {
+        size_t hist[257] = {0};
+        for (uint32_t i = 0; i < n; ++i) hist[((k0[i] >> shift) & 0xff) + 1]++;
+        for (int b = 0; b < 256; ++b) hist[b + 1] += hist[b];
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            size_t d = hist[(k0[i] >> shift) & 0xff]++;
+            k1[d] = k0[i];
+            v1[d] = v0[i];
+        }
+        uint64_t* tk = k0; k0 = k1; k1 = tk;
+        uint32_t* tv = v0; v0 = v1; v1 = tv;
+    }
+    rro_emit_hierarchy64(k0, v0, n, nodes);
+    rro_fit_mesh(nodes, n, verts, sf, idx);
+    if (restructure) rro_restructure(nodes, n);
+    if (sorted_codes) memcpy(sorted_codes, k0, sizeof(uint64_t) * (size_t)n);
+    if (sorted_refs) memcpy(sorted_refs, v0, sizeof(uint32_t) * (size_t)n);
+    free(k0); free(k1); free(v0); free(v1);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -71,6 +71,13 @@ void rro_restructure_round(rro_node* nodes, uint32_t n, uint32_t min_prims);
 void rro_build_blas(const float* verts, uint32_t stride_floats, const uint32_t* idx, uint32_t n, int restructure,
                     rro_node* nodes, uint32_t* sorted_codes, uint32_t* sorted_refs);
 
+/* 63-bit Morton extension (21 bits per axis; dx/kernels/build_hlbvh_fallback.hlsl:95-108 is the reference's only trace of it). */
+void rro_morton_codes63(const float* verts, uint32_t stride_floats, const uint32_t* idx, uint32_t n,
+                        const float smin[3], const float smax[3], uint64_t* codes);
+void rro_emit_hierarchy64(const uint64_t* sorted_codes, const uint32_t* sorted_refs, uint32_t n, rro_node* nodes);
+void rro_build_blas63(const float* verts, uint32_t stride_floats, const uint32_t* idx, uint32_t n, int restructure,
+                      rro_node* nodes, uint64_t* sorted_codes, uint32_t* sorted_refs);
+
 /* TLAS over instances. blas_roots[i] -> node 0 of instance i's BLAS, blas_tris[i] = its triangle count;
  * transforms = 12 floats per instance (row-major 3x4).  out_transforms = 2n x 12 floats
  * ([2i]=inverse, [2i+1]=forward).  reference_corner_quirk=1 reproduces the reference's

@@ -30,6 +30,7 @@ RR_INVALID_VALUE = 0xFFFFFFFF
 RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK = 1, 2
 RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY = 3
 RR_CUDA_OPTION_SORT_RAYS = 4
+RR_CUDA_OPTION_MORTON_BITS = 5
 
 _vp = C.c_void_p
 

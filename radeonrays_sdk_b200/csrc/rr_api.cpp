@@ -258,7 +258,7 @@ RRError rrGetGeometryBuildMemoryRequirements(RRContext context, const RRGeometry
     {
         MeshDesc m{};
         if (RRError e = mesh_from_input(build_input, m)) return e;
-        const BlasLayout L = blas_layout(m.triangle_count, wants_restructure(build_options));
+        const BlasLayout L = blas_layout(m.triangle_count, wants_restructure(build_options), C(context)->dev.morton63);
         memory_requirements->result_buffer_size           = L.result_total;
         memory_requirements->temporary_build_buffer_size  = L.scratch_total;
         // work lists of the staged refit (the dx backend reports 4 N, dx/update_hlbvh.cpp:59-63; vlk reports 0).  An update
@@ -290,7 +290,7 @@ RRError rrCmdBuildGeometry(RRContext context, RRBuildOperation build_operation, 
         {
             if (!temporary_buffer) return RR_ERROR_INVALID_PARAMETER;
             const bool       restructure = wants_restructure(build_options);
-            const BlasLayout L           = blas_layout(m.triangle_count, restructure);
+            const BlasLayout L           = blas_layout(m.triangle_count, restructure, ctx->dev.morton63);
             if (D(temporary_buffer)->bytes_available() < L.scratch_total || D(geometry_buffer)->bytes_available() < L.result_total)
                 throw std::runtime_error("geometry build: buffer smaller than rrGetGeometryBuildMemoryRequirements reported");
             void* scratch = D(temporary_buffer)->ptr();
@@ -628,6 +628,10 @@ RRError rrCudaSetOption(RRContext context, RRCudaOption option, int value)
     {
     case RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND: C(context)->first_found_tie_rule = value != 0; return RR_SUCCESS;
     case RR_CUDA_OPTION_REFERENCE_TRANSFORM_AABB_QUIRK: C(context)->reference_corner_quirk = value != 0; return RR_SUCCESS;
+    case RR_CUDA_OPTION_MORTON_BITS:
+        if (value != 30 && value != 63) return RR_ERROR_INVALID_PARAMETER;
+        C(context)->dev.morton63 = value == 63;
+        return RR_SUCCESS;
     case RR_CUDA_OPTION_SORT_RAYS: C(context)->dev.sort_rays = value != 0; return RR_SUCCESS;
     case RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY: C(context)->dev.refit_list_capacity = value > 0 ? (uint32_t)value : 0u; return RR_SUCCESS;
     default: return RR_ERROR_INVALID_PARAMETER;
@@ -710,10 +714,10 @@ RRError rrCudaGetLaunchCount(RRContext context, uint64_t* launches)
 RRError rrCudaDebugGetBuildScratchLayout(RRContext context, uint32_t triangle_count, RRCudaBuildScratchLayout* layout)
 {
     if (!context || !layout || !triangle_count) return RR_ERROR_INVALID_PARAMETER;
-    const BlasLayout L         = blas_layout(triangle_count, false);
+    const BlasLayout L         = blas_layout(triangle_count, false, C(context)->dev.morton63);
     layout->scene_aabb_offset   = L.aabb_off;
     layout->morton_codes_offset = L.codes_off;
-    layout->sorted_codes_offset = L.sorted_codes_off;
+    layout->sorted_codes_offset = L.morton63 ? L.codes64_off : L.sorted_codes_off;   // u64[N] with RR_CUDA_OPTION_MORTON_BITS = 63
     layout->sorted_refs_offset  = L.tail_refs_off;  // inside the GEOMETRY buffer
     layout->sort_tmp_values_offset = L.sort_off + L.sort.tmp_vals_off;
     return RR_SUCCESS;

@@ -373,10 +373,11 @@ __device__ __forceinline__ MergeOut group_merge(StoreNode&& store_node, int n, i
     const uint32_t vmask = cnt >= 32 ? full : ((1u << cnt) - 1u);
     const uint32_t below = (1u << lane) - 1u, above = ~((2u << lane) - 1u);
     if (!valid) D = 0;
-    // lanes whose delta is smaller than mine (deltas fit 6 bits: radix compare over bit planes)
+    // lanes whose delta is smaller than mine (deltas fit 7 bits -- 0..63 for 30-bit codes, 0..95 for the 63-bit extension:
+    // radix compare over bit planes)
     uint32_t lt = 0, eq = full;
 #pragma unroll
-    for (int bit = 5; bit >= 0; --bit)
+    for (int bit = 6; bit >= 0; --bit)
     {
         const bool     mine = (D >> bit) & 1;
         const uint32_t B    = __ballot_sync(full, mine);
@@ -1443,10 +1444,11 @@ static size_t emit_list_bytes(uint32_t n)
     return n <= (uint32_t)kEmitWindow ? 0 : sizeof(uint32_t) * (emit_list_words(windows) + emit_list_words((windows + kUpperFan - 1) / kUpperFan));
 }
 
-BlasLayout blas_layout(uint32_t n, bool restructure)
+BlasLayout blas_layout(uint32_t n, bool restructure, bool morton63)
 {
     BlasLayout L;
     L.n    = n;
+    L.morton63 = morton63;
     L.sort = sort_layout(n);
     size_t off = 0;
     // scene AABB: min words preset to 0xFF.., max words to 0
@@ -1458,6 +1460,17 @@ BlasLayout blas_layout(uint32_t n, bool restructure)
     L.sorted_refs_off  = 0;  // the sorted primitive ids go straight into the geometry buffer's tail (tail_refs_off)
     L.sort_off = off; off += L.sort.total;
     L.lists_off = off; off += align_up(emit_list_bytes(n), 256);
+    if (morton63)
+    {   // codes_off holds the low words, sorted_codes_off is unused
+        const size_t w = align_up(sizeof(uint32_t) * (size_t)n, 256);
+        L.hi_off = off; off += w;
+        L.sorted_lo_off = off; off += w;
+        L.perm1_off = off; off += w;
+        L.hi_gathered_off = off; off += w;
+        L.sorted_hi_off = off; off += w;
+        L.perm2_off = off; off += w;
+        L.codes64_off = off; off += 2 * w;
+    }
     L.treelet_off  = 0;
     L.treelet_size = restructure ? treelet_scratch_size(n) : 0;
     L.scratch_total = std::max(off, L.treelet_size);
@@ -1468,6 +1481,75 @@ BlasLayout blas_layout(uint32_t n, bool restructure)
     L.tail_refs_off   = roff; roff += align_up(sizeof(uint32_t) * (size_t)n, 256);
     L.result_total    = roff;
     return L;
+}
+
+// ---- 63-bit Morton extension (BASELINE north_star "30/63-bit Morton codes"; RR_CUDA_OPTION_MORTON_BITS = 63) ----------------------
+// The reference ships 30-bit codes only (its DX fallback keeps a compiled-out 64-bit delta(), build_hlbvh_fallback.hlsl:16,95-108),
+// so this is an extension, defined in oracle/rr_oracle.c (rro_build_blas63) and bit-exact against it: the 30-bit pipeline with 21
+// bits per axis.  Built from the pieces that exist: the code is kept as two 32-bit words, the stable 64-bit sort is two stable
+// 32-bit onesweep sorts (low word, then high word of the low-sorted sequence), and the hierarchy is emitted by the refit's
+// re-emission path, which needs only delta(j, j+1) and the sorted primitive ids in the geometry buffer's tail.
+__device__ __forceinline__ uint64_t expand_bits21(uint32_t v)
+{
+    uint64_t x = v & 0x1FFFFFu;
+    x = (x | (x << 32)) & 0x001F00000000FFFFull;
+    x = (x | (x << 16)) & 0x001F0000FF0000FFull;
+    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+__global__ void __launch_bounds__(256)
+    k_morton63(MeshDesc m, const uint32_t* __restrict__ g_aabb, uint32_t* __restrict__ lo, uint32_t* __restrict__ hi)
+{
+    float3 smin, smax;
+    load_scene_box(g_aabb, smin, smax);
+    const float3   ext = make_float3(smax.x - smin.x, smax.y - smin.y, smax.z - smin.z);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m.triangle_count; i += stride)
+    {
+        uint32_t i0, i1, i2;
+        tri_indices(m, i, i0, i1, i2);
+        const float3 v0 = ld3(m.vertices + (size_t)i0 * m.stride_floats), v1 = ld3(m.vertices + (size_t)i1 * m.stride_floats),
+                     v2 = ld3(m.vertices + (size_t)i2 * m.stride_floats);
+        const float3 bmin = min3(min3(v0, v1), v2), bmax = max3(max3(v0, v1), v2);
+        const float3 c  = make_float3(0.5f * (bmin.x + bmax.x), 0.5f * (bmin.y + bmax.y), 0.5f * (bmin.z + bmax.z));
+        const float  px = (c.x - smin.x) / ext.x, py = (c.y - smin.y) / ext.y, pz = (c.z - smin.z) / ext.z;
+        const float  x = fminf(fmaxf(px * 2097152.0f, 0.0f), 2097151.0f);
+        const float  y = fminf(fmaxf(py * 2097152.0f, 0.0f), 2097151.0f);
+        const float  z = fminf(fmaxf(pz * 2097152.0f, 0.0f), 2097151.0f);
+        const uint64_t code = (expand_bits21((uint32_t)x) << 2) | (expand_bits21((uint32_t)y) << 1) | expand_bits21((uint32_t)z);
+        lo[i] = (uint32_t)code;
+        hi[i] = (uint32_t)(code >> 32);
+    }
+}
+__global__ void __launch_bounds__(256) k_gather_u32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ perm, uint32_t* __restrict__ dst, uint32_t n)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[perm[i]];
+}
+// Final order k: position perm2[k] of the low-sorted sequence, i.e. primitive perm1[perm2[k]]; writes the sorted 64-bit codes, the
+// sorted primitive ids and delta(k, k+1) (dx/kernels/build_hlbvh_fallback.hlsl:95-108 with true clz) into the geometry buffer's tail.
+__global__ void __launch_bounds__(256)
+    k_finish63(uint32_t n, const uint32_t* __restrict__ perm1, const uint32_t* __restrict__ perm2, const uint32_t* __restrict__ sorted_lo,
+               const uint32_t* __restrict__ sorted_hi, uint32_t* __restrict__ refs, uint8_t* __restrict__ deltas, uint64_t* __restrict__ codes64,
+               uint32_t* __restrict__ karras)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) *karras = 1u;  // the tree about to be emitted is the Karras tree of these deltas
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    {
+        const uint32_t p2 = perm2[k];
+        const uint64_t c  = ((uint64_t)sorted_hi[k] << 32) | sorted_lo[p2];
+        refs[k]    = perm1[p2];
+        codes64[k] = c;
+        int d = 0;
+        if (k + 1 < n)
+        {
+            const uint64_t cn = ((uint64_t)sorted_hi[k + 1] << 32) | sorted_lo[perm2[k + 1]];
+            const uint64_t x  = c ^ cn;
+            d = x ? __clzll((long long)x) : 64 + __clz((int)(k ^ (k + 1)));
+        }
+        deltas[k] = (uint8_t)d;
+    }
 }
 
 static void reset_build_scratch(cudaStream_t s, char* sc, size_t aabb_off, const SortLayout& sl, size_t sort_off)
@@ -1493,11 +1575,35 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
 
     reset_build_scratch(s, sc, L.aabb_off, L.sort, L.sort_off);
     k_scene_aabb<<<grid_for(dev, n, 256, 8), 256, 0, s>>>(mesh, g_aabb);
-    k_morton<false><<<grid_for(dev, n, 256, 8), 256, 0, s>>>(mesh, nullptr, n, g_aabb, codes, sort_hist_ptr(L.sort, sort_scratch));
-    *dev.launches += 2;
-    sort_pairs(dev, s, L.sort, sort_scratch, codes, nullptr, sorted_codes, sorted_refs);
     EmitParams p{};
-    p.codes = sorted_codes; p.refs = sorted_refs; p.n = n; p.nodes = nodes; p.mesh = mesh;
+    if (L.morton63)
+    {
+        uint32_t* hi = reinterpret_cast<uint32_t*>(sc + L.hi_off), *sorted_lo = reinterpret_cast<uint32_t*>(sc + L.sorted_lo_off);
+        uint32_t* perm1 = reinterpret_cast<uint32_t*>(sc + L.perm1_off), *hi_g = reinterpret_cast<uint32_t*>(sc + L.hi_gathered_off);
+        uint32_t* sorted_hi = reinterpret_cast<uint32_t*>(sc + L.sorted_hi_off), *perm2 = reinterpret_cast<uint32_t*>(sc + L.perm2_off);
+        char*     geom = reinterpret_cast<char*>(nodes);
+        const int grid = grid_for(dev, n, 256, 8);
+        k_morton63<<<grid, 256, 0, s>>>(mesh, g_aabb, codes, hi);
+        sort_histogram(dev, s, L.sort, sort_scratch, codes);
+        sort_pairs(dev, s, L.sort, sort_scratch, codes, nullptr, sorted_lo, perm1);            // stable by the low word
+        k_gather_u32<<<grid, 256, 0, s>>>(hi, perm1, hi_g, n);
+        sort_reset(dev, s, L.sort, sort_scratch);
+        sort_histogram(dev, s, L.sort, sort_scratch, hi_g);
+        sort_pairs(dev, s, L.sort, sort_scratch, hi_g, nullptr, sorted_hi, perm2);             // then stable by the high word
+        k_finish63<<<grid, 256, 0, s>>>(n, perm1, perm2, sorted_lo, sorted_hi, sorted_refs, reinterpret_cast<uint8_t*>(geom + L.tail_deltas_off),
+                                        reinterpret_cast<uint64_t*>(sc + L.codes64_off), reinterpret_cast<uint32_t*>(geom + L.tail_off));
+        *dev.launches += 4;
+        p.codes = nullptr; p.from_tail = true;   // emission from the tail's deltas and ids, as a refit does
+    }
+    else
+    {
+        k_morton<false><<<grid_for(dev, n, 256, 8), 256, 0, s>>>(mesh, nullptr, n, g_aabb, codes, sort_hist_ptr(L.sort, sort_scratch));
+        *dev.launches += 1;
+        sort_pairs(dev, s, L.sort, sort_scratch, codes, nullptr, sorted_codes, sorted_refs);
+        p.codes = sorted_codes;
+    }
+    *dev.launches += 1;
+    p.refs = sorted_refs; p.n = n; p.nodes = nodes; p.mesh = mesh;
     p.lists = reinterpret_cast<uint32_t*>(sc + L.lists_off);
     p.masks = reinterpret_cast<uint32_t*>(sc + L.sort_off + L.sort.tmp_vals_off);  // the sort's ping-pong buffer is dead now
     char* geom  = reinterpret_cast<char*>(nodes);

@@ -98,6 +98,7 @@ struct DeviceInfo
     int      sm_count    = 148;
     size_t   l2_bytes    = 0;
     uint64_t* launches   = nullptr;  // per-context launch counter (host side)
+    bool      morton63   = false;    // RR_CUDA_OPTION_MORTON_BITS = 63: geometry builds use 21 bits per axis (extension)
     bool      sort_rays  = false;    // RR_CUDA_OPTION_SORT_RAYS: bin the rays of every rrCmdIntersect on the device before tracing
     uint32_t  refit_list_capacity = 0;  // test hook (RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY): 0 = sized by the library
     uint32_t* error_word = nullptr;  // device-visible (host-mapped) word the kernels OR error bits into; checked by rrWaitEvent
@@ -136,6 +137,9 @@ struct BlasLayout
     uint32_t   n = 0;
     size_t     aabb_off = 0, codes_off = 0, sorted_codes_off = 0, sorted_refs_off = 0, sort_off = 0, lists_off = 0;
     size_t     treelet_off = 0, treelet_size = 0;
+    // 63-bit Morton builds: low / high code words, the two permutations of the two-stage sort, the sorted 64-bit codes
+    bool       morton63 = false;
+    size_t     hi_off = 0, sorted_lo_off = 0, perm1_off = 0, hi_gathered_off = 0, sorted_hi_off = 0, perm2_off = 0, codes64_off = 0;
     SortLayout sort;
     size_t     scratch_total = 0, result_total = 0;
     // private tail of the geometry buffer, after the VkBvhNode[2N-1] array: what a refit needs to re-run the closed-form
@@ -143,7 +147,7 @@ struct BlasLayout
     // sorted leaf, 1 B | primitive id per sorted leaf, 4 B]
     size_t     tail_off = 0, tail_deltas_off = 0, tail_refs_off = 0;
 };
-BlasLayout blas_layout(uint32_t triangle_count, bool restructure);
+BlasLayout blas_layout(uint32_t triangle_count, bool restructure, bool morton63 = false);
 void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, const BlasLayout& L, void* scratch, Node* nodes,
                 bool restructure);
 size_t update_scratch_size(uint32_t triangle_count);

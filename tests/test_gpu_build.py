@@ -4,7 +4,7 @@ import pytest
 
 from oracle import binding as O
 from radeonrays_sdk_b200 import api, workloads as W
-from helpers import assert_nodes_equal
+from helpers import assert_hits_equal, assert_nodes_equal
 
 pytestmark = pytest.mark.gpu
 
@@ -264,3 +264,51 @@ def test_refit_hand_over_lists_never_drop_a_subtree(engine, sponza, shape):
     assert_nodes_equal(g.nodes(), O.refit(before, moved, idx), what="refit with overflowing hand-over lists")
     engine.update_geometry(g, pos)                              # and back, with the default capacities
     assert_nodes_equal(g.nodes(), O.refit(before, pos, idx), what="refit back")
+
+
+@pytest.mark.parametrize("mesh", ["cornell", "sponza", "duplicates", "heightfield_300k"])
+def test_morton63_build(engine, sponza, cornell, mesh):
+    """RR_CUDA_OPTION_MORTON_BITS = 63 (BASELINE north_star "30/63-bit Morton codes"; an extension, the reference ships 30-bit codes
+    only): sorted 63-bit codes, sorted primitive order and every node bit-equal to the oracle's rro_build_blas63; a refit afterwards
+    re-emits from the same deltas; the quality build restructures it like any other tree; traces agree with the oracle."""
+    import torch
+    if mesh == "cornell":
+        pos, idx, _ = cornell
+    elif mesh == "sponza":
+        pos, idx, _ = sponza
+    elif mesh == "duplicates":       # every triangle twice + a cluster of identical centroids: equal 63-bit codes, index tie-break
+        rng = np.random.default_rng(4)
+        base = rng.random((3000, 3), dtype=np.float32)
+        tri = rng.integers(0, 3000, (5000, 3)).astype(np.uint32)
+        pos, idx = base, np.concatenate([tri, tri, np.repeat(tri[:1], 700, 0)]).astype(np.uint32)
+    else:
+        pos, idx = W.heightfield_mesh(500, 300, t=0.0)
+    n = idx.shape[0]
+    ctx = engine.ctx
+    ctx.set_option(api.RR_CUDA_OPTION_MORTON_BITS, 63)
+    try:
+        g = engine.build_geometry(pos, idx)                       # fast build
+        L = ctx.build_scratch_layout(n)
+        codes = g.d_temp[L.sorted_codes_offset: L.sorted_codes_offset + 8 * n].cpu().numpy().view(np.uint64)
+        refs = g.d_nodes[L.sorted_refs_offset: L.sorted_refs_offset + 4 * n].cpu().numpy().view(np.uint32)
+        want, wc, wr = O.build_blas63(pos, idx)
+        assert np.array_equal(codes, wc), "sorted 63-bit Morton codes"
+        assert np.array_equal(refs, wr), "sorted primitive order"
+        assert_nodes_equal(g.nodes(), want, what="63-bit build")
+        assert O.check_consistency(g.nodes())
+        moved = (pos * np.float32(1.1) + np.float32(0.3)).astype(np.float32)
+        engine.update_geometry(g, moved)
+        assert_nodes_equal(g.nodes(), O.refit(want, moved, idx), what="refit of a 63-bit build")
+        if mesh in ("sponza", "duplicates"):
+            gq = engine.build_geometry(pos, idx, build_flags=0)   # quality build on top of the 63-bit tree
+            wq, _, _ = O.build_blas63(pos, idx, restructure=True)
+            assert_nodes_equal(gq.nodes(), wq, what="63-bit quality build")
+    finally:
+        ctx.set_option(api.RR_CUDA_OPTION_MORTON_BITS, 30)
+    if mesh == "sponza":
+        rays = W.sponza_primary_rays(200, 120)
+        engine.update_geometry(g, pos)
+        assert_hits_equal(engine.intersect(g, rays), O.trace(want, rays), what="trace of a 63-bit build", mesh=(pos, idx), rays=rays)
+        # and the option is back at 30: a fresh build equals the reference-order tree again
+        g30 = engine.build_geometry(pos, idx)
+        assert_nodes_equal(g30.nodes(), O.build_blas(pos, idx)[0], what="30-bit build after the option was reset")
