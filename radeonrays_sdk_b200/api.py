@@ -237,6 +237,15 @@ class Context:
         gi._mesh = mesh
         return gi
 
+    @staticmethod
+    def geometry_input_multi(meshes):
+        """meshes: list of (vertices_ptr, vertex_count, vertex_stride, indices_ptr, triangle_count, index_type) -- a geometry made
+        of several triangle meshes (primitive_count > 1; prim_id = running triangle index over the meshes)."""
+        arr = (RRTriangleMeshPrimitive * len(meshes))(*[RRTriangleMeshPrimitive(*m) for m in meshes])
+        gi = RRGeometryBuildInput(RR_PRIMITIVE_TYPE_TRIANGLE_MESH, len(meshes), C.cast(arr, C.POINTER(RRTriangleMeshPrimitive)))
+        gi._mesh = arr
+        return gi
+
     def geometry_requirements(self, geometry_input, options=None):
         req = RRMemoryRequirements()
         check(self.lib.rrGetGeometryBuildMemoryRequirements(self.handle, C.byref(geometry_input),

@@ -181,21 +181,36 @@ static bool wants_restructure(const RRBuildOptions* o)
     return o && (o->build_flags & RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD) == 0;
 }
 
-// GetTriangleMeshBuildInfo, radeonrays.cpp:59-74 (one mesh per geometry, vlk/intersector.cpp:110,146)
-static RRError mesh_from_input(const RRGeometryBuildInput* in, MeshDesc& m)
+// GetTriangleMeshBuildInfo, radeonrays.cpp:59-74.  The reference builds one mesh per geometry (vlk/intersector.cpp:110,146 assert
+// primitive_count == 1); here up to kMaxMeshesPerGeometry meshes are accepted and concatenated on the device (rr_build.cu
+// merge_meshes): prim_id = running triangle index over the meshes in input order.
+static RRError meshes_from_input(const RRGeometryBuildInput* in, MeshGroup& g)
 {
     if (in->primitive_type != RR_PRIMITIVE_TYPE_TRIANGLE_MESH) return RR_ERROR_NOT_IMPLEMENTED;
     if (in->primitive_count == 0 || !in->triangle_mesh_primitives) return RR_ERROR_INVALID_PARAMETER;
-    if (in->primitive_count != 1) return RR_ERROR_NOT_IMPLEMENTED;
-    const RRTriangleMeshPrimitive& p = in->triangle_mesh_primitives[0];
-    if (p.index_type != RR_INDEX_TYPE_UINT32 && p.index_type != RR_INDEX_TYPE_UINT16) return RR_ERROR_INVALID_PARAMETER;
-    if (p.triangle_count == 0 || (p.vertex_stride & 3u) || p.vertex_stride < 12) return RR_ERROR_INVALID_PARAMETER;
-    m.vertices       = p.vertices ? reinterpret_cast<const float*>(D(p.vertices)->ptr()) : nullptr;
-    m.vertex_count   = p.vertex_count;
-    m.stride_floats  = p.vertex_stride >> 2;
-    m.indices        = p.triangle_indices ? reinterpret_cast<const uint32_t*>(D(p.triangle_indices)->ptr()) : nullptr;
-    m.triangle_count = p.triangle_count;
-    m.index16        = p.index_type == RR_INDEX_TYPE_UINT16 ? 1u : 0u;  // beyond the reference, which reads 32-bit indices whatever index_type says
+    if (in->primitive_count > (uint32_t)kMaxMeshesPerGeometry) return RR_ERROR_NOT_IMPLEMENTED;
+    g.count = in->primitive_count;
+    uint64_t tris = 0, verts = 0;
+    for (uint32_t k = 0; k < g.count; ++k)
+    {
+        const RRTriangleMeshPrimitive& p = in->triangle_mesh_primitives[k];
+        if (p.index_type != RR_INDEX_TYPE_UINT32 && p.index_type != RR_INDEX_TYPE_UINT16) return RR_ERROR_INVALID_PARAMETER;
+        if (p.triangle_count == 0 || (p.vertex_stride & 3u) || p.vertex_stride < 12) return RR_ERROR_INVALID_PARAMETER;
+        MeshDesc& m      = g.mesh[k];
+        m.vertices       = p.vertices ? reinterpret_cast<const float*>(D(p.vertices)->ptr()) : nullptr;
+        m.vertex_count   = p.vertex_count;
+        m.stride_floats  = p.vertex_stride >> 2;
+        m.indices        = p.triangle_indices ? reinterpret_cast<const uint32_t*>(D(p.triangle_indices)->ptr()) : nullptr;
+        m.triangle_count = p.triangle_count;
+        m.index16        = p.index_type == RR_INDEX_TYPE_UINT16 ? 1u : 0u;  // beyond the reference, which reads 32-bit indices whatever index_type says
+        g.tri_first[k]   = (uint32_t)tris;
+        g.vert_first[k]  = (uint32_t)verts;
+        tris += p.triangle_count;
+        verts += p.vertex_count;
+    }
+    if (tris > 0x3FFFFFFFull || verts > 0xFFFFFFFFull) return RR_ERROR_INVALID_PARAMETER;
+    g.tri_first[g.count]  = (uint32_t)tris;
+    g.vert_first[g.count] = (uint32_t)verts;
     return RR_SUCCESS;
 }
 }  // namespace rr
@@ -256,14 +271,14 @@ RRError rrGetGeometryBuildMemoryRequirements(RRContext context, const RRGeometry
     if (!context || !build_input || !memory_requirements) return RR_ERROR_INVALID_PARAMETER;
     try
     {
-        MeshDesc m{};
-        if (RRError e = mesh_from_input(build_input, m)) return e;
-        const BlasLayout L = blas_layout(m.triangle_count, wants_restructure(build_options), C(context)->dev.morton63);
+        MeshGroup g{};
+        if (RRError e = meshes_from_input(build_input, g)) return e;
+        const BlasLayout L = blas_layout(g.triangles(), wants_restructure(build_options), C(context)->dev.morton63);
         memory_requirements->result_buffer_size           = L.result_total;
-        memory_requirements->temporary_build_buffer_size  = L.scratch_total;
+        memory_requirements->temporary_build_buffer_size  = merge_scratch_size(g) + L.scratch_total;
         // work lists of the staged refit (the dx backend reports 4 N, dx/update_hlbvh.cpp:59-63; vlk reports 0).  An update
-        // recorded without a temporary buffer still works, as one slower kernel.
-        memory_requirements->temporary_update_buffer_size = update_scratch_size(m.triangle_count);
+        // recorded without a temporary buffer still works, as one slower kernel (single-mesh geometries only).
+        memory_requirements->temporary_update_buffer_size = merge_scratch_size(g) + update_scratch_size(g.triangles());
     }
     catch (...) { return map_exception(); }
     return RR_SUCCESS;
@@ -278,32 +293,43 @@ RRError rrCmdBuildGeometry(RRContext context, RRBuildOperation build_operation, 
     try
     {
         Context* ctx = C(context);
-        MeshDesc m{};
-        if (RRError e = mesh_from_input(build_input, m)) return e;
-        if (!m.vertices || !m.indices || !geometry_buffer) return RR_ERROR_INVALID_PARAMETER;
+        MeshGroup g{};
+        if (RRError e = meshes_from_input(build_input, g)) return e;
+        if (!geometry_buffer) return RR_ERROR_INVALID_PARAMETER;
+        for (uint32_t k = 0; k < g.count; ++k)
+            if (!g.mesh[k].vertices || !g.mesh[k].indices || !aligned_to(g.mesh[k].vertices, 4) || !aligned_to(g.mesh[k].indices, g.mesh[k].index16 ? 2 : 4))
+                return RR_ERROR_INVALID_PARAMETER;
         Node*            nodes = reinterpret_cast<Node*>(D(geometry_buffer)->ptr());
-        if (!aligned_to(nodes, 64) || (temporary_buffer && !aligned_to(D(temporary_buffer)->ptr(), 16)) || !aligned_to(m.vertices, 4) ||
-            !aligned_to(m.indices, m.index16 ? 2 : 4))
-            return RR_ERROR_INVALID_PARAMETER;
-        const DeviceInfo dev   = ctx->dev;
+        if (!aligned_to(nodes, 64) || (temporary_buffer && !aligned_to(D(temporary_buffer)->ptr(), 16))) return RR_ERROR_INVALID_PARAMETER;
+        const DeviceInfo dev     = ctx->dev;
+        const uint32_t   n       = g.triangles();
+        const size_t     merged  = merge_scratch_size(g);   // 0 for a single mesh
         if (build_operation == RR_BUILD_OPERATION_BUILD)
         {
             if (!temporary_buffer) return RR_ERROR_INVALID_PARAMETER;
             const bool       restructure = wants_restructure(build_options);
-            const BlasLayout L           = blas_layout(m.triangle_count, restructure, ctx->dev.morton63);
-            if (D(temporary_buffer)->bytes_available() < L.scratch_total || D(geometry_buffer)->bytes_available() < L.result_total)
+            const BlasLayout L           = blas_layout(n, restructure, ctx->dev.morton63);
+            if (D(temporary_buffer)->bytes_available() < merged + L.scratch_total || D(geometry_buffer)->bytes_available() < L.result_total)
                 throw std::runtime_error("geometry build: buffer smaller than rrGetGeometryBuildMemoryRequirements reported");
-            void* scratch = D(temporary_buffer)->ptr();
-            S(command_stream)->commands.push_back([=](cudaStream_t s) { build_blas(dev, s, m, L, scratch, nodes, restructure); });
+            char* scratch = D(temporary_buffer)->ptr();
+            S(command_stream)->commands.push_back([=](cudaStream_t s) {
+                const MeshDesc m = merge_meshes(dev, s, g, scratch);
+                build_blas(dev, s, m, L, scratch + merged, nodes, restructure);
+            });
         }
         else
-        {   // UPDATE: the temporary buffer is optional (the reference's Vulkan backend ignores it, vlk/intersector.cpp:176-204)
+        {   // UPDATE: the temporary buffer is optional for a single mesh (the reference's Vulkan backend ignores it,
+            // vlk/intersector.cpp:176-204); a multi-mesh geometry needs it for the merged arrays.
             // the update reads the tail of the geometry buffer (rr_build.cu update_blas): the whole result buffer must be there
-            if (D(geometry_buffer)->bytes_available() < blas_layout(m.triangle_count, false).result_total)
+            if (D(geometry_buffer)->bytes_available() < blas_layout(n, false).result_total)
                 throw std::runtime_error("geometry update: buffer smaller than rrGetGeometryBuildMemoryRequirements reported");
-            void*        scratch       = temporary_buffer ? D(temporary_buffer)->ptr() : nullptr;
+            char*        scratch       = temporary_buffer ? D(temporary_buffer)->ptr() : nullptr;
             const size_t scratch_bytes = temporary_buffer ? D(temporary_buffer)->bytes_available() : 0;
-            S(command_stream)->commands.push_back([=](cudaStream_t s) { update_blas(dev, s, m, nodes, scratch, scratch_bytes); });
+            if (merged && scratch_bytes < merged) return RR_ERROR_INVALID_PARAMETER;
+            S(command_stream)->commands.push_back([=](cudaStream_t s) {
+                const MeshDesc m = merge_meshes(dev, s, g, scratch);
+                update_blas(dev, s, m, nodes, scratch ? scratch + merged : nullptr, scratch_bytes - merged);
+            });
         }
     }
     catch (...) { return map_exception(); }

@@ -1552,6 +1552,46 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---- multi-mesh geometries: concatenate on the device, then build / refit as one mesh -----------------------------------------
+__global__ void __launch_bounds__(256) k_merge_meshes(MeshGroup g, float* __restrict__ out_v, uint32_t* __restrict__ out_i)
+{
+    const uint32_t tris = g.tri_first[g.count], verts = g.vert_first[g.count];
+    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t t = t0; t < tris; t += stride)
+    {
+        uint32_t k = 0;
+        while (t >= g.tri_first[k + 1]) ++k;
+        uint32_t i0, i1, i2;
+        tri_indices(g.mesh[k], t - g.tri_first[k], i0, i1, i2);
+        out_i[3 * (size_t)t]     = i0 + g.vert_first[k];
+        out_i[3 * (size_t)t + 1] = i1 + g.vert_first[k];
+        out_i[3 * (size_t)t + 2] = i2 + g.vert_first[k];
+    }
+    for (uint32_t v = t0; v < verts; v += stride)
+    {
+        uint32_t k = 0;
+        while (v >= g.vert_first[k + 1]) ++k;
+        const float3 p = ld3(g.mesh[k].vertices + (size_t)(v - g.vert_first[k]) * g.mesh[k].stride_floats);
+        out_v[3 * (size_t)v] = p.x; out_v[3 * (size_t)v + 1] = p.y; out_v[3 * (size_t)v + 2] = p.z;
+    }
+}
+size_t merge_scratch_size(const MeshGroup& g)
+{
+    return g.count <= 1 ? 0 : align_up(12 * (size_t)g.vertices(), 256) + align_up(12 * (size_t)g.triangles(), 256);
+}
+MeshDesc merge_meshes(const DeviceInfo& dev, cudaStream_t s, const MeshGroup& g, void* scratch)
+{
+    if (g.count <= 1) return g.mesh[0];
+    float*    out_v = reinterpret_cast<float*>(scratch);
+    uint32_t* out_i = reinterpret_cast<uint32_t*>(static_cast<char*>(scratch) + align_up(12 * (size_t)g.vertices(), 256));
+    k_merge_meshes<<<grid_for(dev, std::max(g.triangles(), g.vertices()), 256, 8), 256, 0, s>>>(g, out_v, out_i);
+    *dev.launches += 1;
+    RR_CUDA_CHECK(cudaGetLastError());
+    MeshDesc m{};
+    m.vertices = out_v; m.vertex_count = g.vertices(); m.stride_floats = 3; m.indices = out_i; m.triangle_count = g.triangles(); m.index16 = 0;
+    return m;
+}
+
 static void reset_build_scratch(cudaStream_t s, char* sc, size_t aabb_off, const SortLayout& sl, size_t sort_off)
 {
     // min words -> 0xFF ; max words -> 0 ; sort bookkeeping -> 0

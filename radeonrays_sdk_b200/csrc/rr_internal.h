@@ -132,6 +132,23 @@ struct MeshDesc
     uint32_t        triangle_count;
     uint32_t        index16;        // 1: indices are 16-bit
 };
+// A geometry made of several triangle meshes (RRGeometryBuildInput::primitive_count > 1; the reference asserts it out,
+// vlk/intersector.cpp:110).  The meshes are concatenated on the device into one vertex / index array at the front of the temporary
+// buffer (k_merge_meshes) and the single-mesh pipeline runs on that; a hit's prim_id is the triangle's running index over the meshes
+// in input order.
+constexpr int kMaxMeshesPerGeometry = 16;
+struct MeshGroup
+{
+    uint32_t count = 1;                           // 1: `mesh[0]` is used as it is, nothing is merged
+    MeshDesc mesh[kMaxMeshesPerGeometry];
+    uint32_t tri_first[kMaxMeshesPerGeometry + 1];   // running triangle / vertex offsets
+    uint32_t vert_first[kMaxMeshesPerGeometry + 1];
+    uint32_t triangles() const { return count == 1 ? mesh[0].triangle_count : tri_first[count]; }
+    uint32_t vertices() const { return count == 1 ? mesh[0].vertex_count : vert_first[count]; }
+};
+size_t   merge_scratch_size(const MeshGroup& g);   // bytes the merged arrays take at the front of the temporary buffer (0 for one mesh)
+MeshDesc merge_meshes(const DeviceInfo& dev, cudaStream_t s, const MeshGroup& g, void* scratch);   // -> the mesh to build / refit
+
 struct BlasLayout
 {
     uint32_t   n = 0;

@@ -312,3 +312,63 @@ def test_morton63_build(engine, sponza, cornell, mesh):
         # and the option is back at 30: a fresh build equals the reference-order tree again
         g30 = engine.build_geometry(pos, idx)
         assert_nodes_equal(g30.nodes(), O.build_blas(pos, idx)[0], what="30-bit build after the option was reset")
+
+
+def test_multi_mesh_geometry(engine, sponza, cornell):
+    """RRGeometryBuildInput::primitive_count > 1 (SURVEY.md section 8f-4; the reference asserts it out, vlk/intersector.cpp:110): three
+    meshes with their own vertex buffers, strides and index types in ONE geometry.  The BLAS must equal the oracle's build of the
+    concatenated mesh, prim_id is the running triangle index, and UPDATE refits from the (moved) separate buffers."""
+    import torch
+    from radeonrays_sdk_b200.host import Geometry, _dev_bytes, _upload
+    pos, idx, first = sponza
+    cpos, cidx, _ = cornell
+    a_idx = idx[first[73]:first[74]]                                             # 13 988 triangles, u32 indices, stride 12
+    b_pos = (cpos * np.float32(20.0) + np.float32([0, 0, 30])).astype(np.float32)  # Cornell box, u16 indices, stride 16
+    b_pad = np.zeros((b_pos.shape[0], 4), np.float32); b_pad[:, :3] = b_pos; b_pad[:, 3] = 7.0
+    c_pos, c_idx = W.single_triangle()
+    c_pos = (c_pos * np.float32(50.0)).astype(np.float32)
+    ctx, dev = engine.ctx, engine.device
+
+    def make(posa, posb_pad, posc):
+        bufs = [_upload(posa, dev), _upload(a_idx, dev), _upload(posb_pad, dev), _upload(cidx.astype(np.uint16), dev), _upload(posc, dev), _upload(c_idx, dev)]
+        p = [ctx.tensor_ptr(t) for t in bufs]
+        gi = ctx.geometry_input_multi([(p[0], posa.shape[0], 12, p[1], a_idx.shape[0], api.RR_INDEX_TYPE_UINT32),
+                                       (p[2], posb_pad.shape[0], 16, p[3], cidx.shape[0], api.RR_INDEX_TYPE_UINT16),
+                                       (p[4], posc.shape[0], 12, p[5], c_idx.shape[0], api.RR_INDEX_TYPE_UINT32)])
+        return gi, bufs
+
+    def concat(posa, posb, posc):
+        allpos = np.concatenate([posa, posb, posc]).astype(np.float32)
+        allidx = np.concatenate([a_idx, cidx + np.uint32(posa.shape[0]), c_idx + np.uint32(posa.shape[0] + posb.shape[0])]).astype(np.uint32)
+        return allpos, allidx
+
+    for flags in (api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD, 0):
+        gi, bufs = make(pos, b_pad, c_pos)
+        opts = api.RRBuildOptions(flags, None)
+        req = ctx.geometry_requirements(gi, opts)
+        g = Geometry()
+        g.engine = engine
+        g.d_temp, g.d_nodes = _dev_bytes(max(req.temporary_build_buffer_size, req.temporary_update_buffer_size), dev), _dev_bytes(req.result_buffer_size, dev)
+        g.p_temp, g.p_nodes = ctx.tensor_ptr(g.d_temp), ctx.tensor_ptr(g.d_nodes)
+        ctx.run(lambda s: ctx.cmd_build_geometry(api.RR_BUILD_OPERATION_BUILD, gi, opts, g.p_temp, g.p_nodes, s))
+        allpos, allidx = concat(pos, b_pos, c_pos)
+        g.triangle_count = allidx.shape[0]
+        want, _, _ = O.build_blas(allpos, allidx, restructure=(flags == 0))
+        assert_nodes_equal(g.nodes(), want, what=f"multi-mesh build flags={flags}")
+        rays = W.random_rays(50_000, allpos.min(0) - 5, allpos.max(0) + 5, seed=23)
+        got = engine.intersect(g, rays)
+        assert_hits_equal(got, O.trace(want, rays), what="multi-mesh trace", mesh=(allpos, allidx), rays=rays)
+        hit = got["inst_id"] != O.INVALID
+        assert (got["prim_id"][hit] >= a_idx.shape[0]).sum() > 50, "hits on the second / third mesh carry running triangle indices"
+        # UPDATE from moved separate buffers
+        moved_a = (pos + np.float32(0.5)).astype(np.float32)
+        moved_b = b_pad.copy(); moved_b[:, :3] *= np.float32(1.1)
+        moved_c = (c_pos * np.float32(0.9)).astype(np.float32)
+        bufs[0].copy_(_upload(moved_a, dev)); bufs[2].copy_(_upload(moved_b, dev)); bufs[4].copy_(_upload(moved_c, dev))
+        ctx.run(lambda s: ctx.cmd_build_geometry(api.RR_BUILD_OPERATION_UPDATE, gi, opts, g.p_temp, g.p_nodes, s))
+        mpos, _ = concat(moved_a, moved_b[:, :3], moved_c)
+        assert_nodes_equal(g.nodes(), O.refit(want, mpos, allidx), what=f"multi-mesh refit flags={flags}")
+    # more meshes than the backend merges, and a non-triangle primitive type: NOT_IMPLEMENTED like the reference
+    many = ctx.geometry_input_multi([(ctx.tensor_ptr(bufs[4]), 3, 12, ctx.tensor_ptr(bufs[5]), 1, api.RR_INDEX_TYPE_UINT32)] * 17)
+    req = api.RRMemoryRequirements()
+    assert ctx.lib.rrGetGeometryBuildMemoryRequirements(ctx.handle, many, None, req) == api.RR_ERROR_NOT_IMPLEMENTED
