@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--check", action="store_true", help="download the BVH and run the oracle's structural check")
     ap.add_argument("--no-refit", action="store_true", help="time the build only")
+    ap.add_argument("--quality", action="store_true", help="build_flags = 0: treelet-restructured tree, generic staged refit")
     args = ap.parse_args()
     eng = Engine(0)
     ctx, dev = eng.ctx, eng.device
@@ -47,11 +48,11 @@ def main():
         g = Geometry()
         g.engine, g.triangle_count, g.vertex_count, g.vertex_stride = eng, n, pos.shape[0], 12
         g.d_vertices, g.d_indices = pos.view(torch.uint8).reshape(-1), idx.view(torch.uint8).reshape(-1)
-        g.options = api.RRBuildOptions(api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD, None)
+        g.options = api.RRBuildOptions(0 if args.quality else api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD, None)
         g.p_vertices, g.p_indices = ctx.tensor_ptr(g.d_vertices), ctx.tensor_ptr(g.d_indices)
         g.input = ctx.geometry_input(g.p_vertices, g.vertex_count, 12, g.p_indices, n)
         g.req = ctx.geometry_requirements(g.input, g.options)
-        g.d_temp, g.d_nodes = _dev_bytes(g.req.temporary_build_buffer_size, dev), _dev_bytes(g.req.result_buffer_size, dev)
+        g.d_temp, g.d_nodes = _dev_bytes(max(g.req.temporary_build_buffer_size, g.req.temporary_update_buffer_size), dev), _dev_bytes(g.req.result_buffer_size, dev)
         g.p_temp, g.p_nodes = ctx.tensor_ptr(g.d_temp), ctx.tensor_ptr(g.d_nodes)
 
         def timed(op):
@@ -81,7 +82,7 @@ def main():
         pos2, _ = heightfield_device(nx, nz, 1.0, dev)
         g.d_vertices.copy_(pos2.view(torch.uint8).reshape(-1))
         ms_refit = timed(api.RR_BUILD_OPERATION_UPDATE) if not args.no_refit else float('nan')
-        out = {"workload": f"height field {nx}x{nz}", "triangles": n, "build_ms": round(ms_build, 4), "build_mtris_per_s": round(n / ms_build / 1e3, 1),
+        out = {"workload": f"height field {nx}x{nz}" + (" (quality build)" if args.quality else ""), "triangles": n, "build_ms": round(ms_build, 4), "build_mtris_per_s": round(n / ms_build / 1e3, 1),
                "build_gbs": round(BUILD_BYTES_PER_TRI * n / ms_build / 1e6, 1), "build_roofline_frac": round(BUILD_BYTES_PER_TRI * n / ms_build / 1e6 / peak, 4),
                "refit_ms": round(ms_refit, 4), "refit_mtris_per_s": round(n / ms_refit / 1e3, 1),
                "refit_gbs": round(REFIT_BYTES_PER_TRI * n / ms_refit / 1e6, 1), "refit_roofline_frac": round(REFIT_BYTES_PER_TRI * n / ms_refit / 1e6 / peak, 4),
