@@ -248,3 +248,62 @@ def test_ray_binning_option_is_bit_identical(engine, sponza, cornell):
     finally:
         engine.ctx.set_option(api.RR_CUDA_OPTION_SORT_RAYS, 0)
     assert_hits_equal(got, O.trace(g.nodes(), diffuse), what="binned diffuse", mesh=(pos, idx), rays=diffuse)
+
+
+def test_degenerate_rays_and_triangles(engine, cornell):
+    """Edge cases the arithmetic must survive exactly like the oracle: rays with zero / denormal / huge direction components
+    (safe_invdir, common.h:166-183), axis-parallel rays, origins on a vertex / edge / face, max_t below min_t, infinite max_t,
+    negative min_t, NaN and infinite components (those packets fail the coherence test and take the per-ray kernel), mixed with
+    ordinary rays in the same 64-ray packets; zero-area and duplicated triangles in the mesh."""
+    pos, idx, _ = cornell
+    pos = np.concatenate([pos, np.array([[0.3, 0.5, 0.1], [0.3, 0.5, 0.1], [0.3, 0.5, 0.1], [0.1, 0.2, 0.0], [0.4, 0.8, 0.0]], np.float32)])
+    nv = pos.shape[0]
+    extra = np.array([[nv - 5, nv - 4, nv - 3],           # a point (zero area)
+                      [nv - 2, nv - 1, nv - 1],           # a segment
+                      idx[3], idx[3], idx[7]], np.uint32)  # duplicates of existing triangles: exact-t ties
+    idx = np.concatenate([idx, extra]).astype(np.uint32)
+    g = engine.build_geometry(pos, idx)
+    nodes = g.nodes()
+    want_nodes, _, _ = O.build_blas(pos, idx)
+    assert_nodes_equal(nodes, want_nodes, what="mesh with degenerate triangles")
+    base = W.cornell_primary_rays(64)                      # 4096 ordinary rays
+    rays = base.copy()
+    rng = np.random.default_rng(12)
+    special = []
+    def ray(o, d, tmin=0.001, tmax=1e5):
+        r = np.zeros(1, W.RAY_DTYPE); r["origin"] = o; r["direction"] = d; r["min_t"] = tmin; r["max_t"] = tmax
+        special.append(r)
+    for d in ((0, 0, -1), (0, 0, 1), (1, 0, 0), (0, -1, 0), (1e-7, 1e-30, -1), (-0.0, 0.0, -1), (1e-5, -1e-5, -1), (3e38, 1, -1),
+              (1e-40, 0, -1), (0, 0, 0), (0, 0, -1e-20)):
+        ray((0.1, 1.0, 3.0), d)
+    ray(pos[0], (0.3, 0.2, -1)); ray(0.5 * (pos[idx[0, 0]] + pos[idx[0, 1]]), (0, 0, -1)); ray(pos[idx[2]].mean(0), (0, 1, 0))
+    ray((0, 1, 3.5), (0, 0, -1), tmin=5.0, tmax=1.0)            # empty interval
+    ray((0, 1, 3.5), (0, 0, -1), tmin=0.0, tmax=np.inf)
+    ray((0, 1, 0.0), (0, 0, -1), tmin=-10.0, tmax=10.0)         # negative min_t: hits behind the origin count
+    ray((0, 1, 3.5), (0, 0, -1), tmin=0.0, tmax=0.0)
+    ray((np.nan, 1, 3.5), (0, 0, -1)); ray((0, 1, 3.5), (np.nan, 0, -1)); ray((0, 1, 3.5), (0, np.inf, -1)); ray((np.inf, 1, 3.5), (0, 0, -1))
+    ray((0, 1, 3.5), (0, 0, -1), tmin=np.nan); ray((0, 1, 3.5), (0, 0, -1), tmax=np.nan)
+    special = np.concatenate(special)
+    at = rng.choice(rays.shape[0], special.shape[0], replace=False)      # scattered among ordinary rays, inside their packets
+    rays[at] = special
+    for query in (CLOSEST, ANY):
+        got = engine.intersect(g, rays, query, FULL)
+        want = O.trace(nodes, rays, query, O.OUTPUT_FULL_HIT)
+        # NaN uv of a hit compares equal bit for bit; ids must agree everywhere
+        assert np.array_equal(got["inst_id"], want["inst_id"]), f"q={query}: hit / miss differs at {np.nonzero(got['inst_id'] != want['inst_id'])[0][:8]}"
+        ok = want["inst_id"] != O.INVALID
+        differ = ok & (got["prim_id"] != want["prim_id"])
+        if query == CLOSEST and differ.any():              # exact-t ties between the duplicated triangles: brute force decides
+            bf, _ = O.brute_force(pos, idx, rays[differ])
+            assert np.array_equal(got["prim_id"][differ], bf["prim_id"])
+        else:
+            assert not differ.any()
+        same = ok & ~differ
+        assert np.array_equal(got["uv"][same].view(np.uint32), want["uv"][same].view(np.uint32))
+    engine.ctx.set_option(api.RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, 1)
+    try:
+        got = engine.intersect(g, rays)
+    finally:
+        engine.ctx.set_option(api.RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, 0)
+    want = O.trace(nodes, rays, tie=O.TIE_FIRST_FOUND)
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), "first-found rule: bit for bit, degenerate rays included"
