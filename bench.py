@@ -433,14 +433,20 @@ def c3_strong(eng, geom, pos, idx, rank, world, timed, resubmitter, count=1 << 2
         ms = timed(go, steps, 2) / steps
         out[name + "_ms"] = round(ms, 4)
         out[name + "_mrays_per_s"] = round(count / ms / 1e3, 1)
-        if world == 1 and name == "diffuse":
-            # the same batch with on-device ray binning (RR_CUDA_OPTION_SORT_RAYS: key pass + radix sort inside the timed call,
-            # bit-identical hits in the client's order; tests/test_gpu_trace.py::test_ray_binning_option_is_bit_identical)
+        if name == "diffuse":
+            # the same batch / shards with on-device ray binning (RR_CUDA_OPTION_SORT_RAYS: key pass + radix sort inside the timed
+            # call, bit-identical hits in the client's order; tests/test_gpu_trace.py::test_ray_binning_option_is_bit_identical)
             ctx.set_option(api.RR_CUDA_OPTION_SORT_RAYS, 1)
-            big = torch.empty(ctx.trace_requirements(count), dtype=torch.uint8, device=dev)
+            big = torch.empty(ctx.trace_requirements(biggest), dtype=torch.uint8, device=dev)
             p_big = ctx.tensor_ptr(big)
-            p_r, p_h = ctx.tensor_ptr(d_rays[name]), ctx.tensor_ptr(local)
-            go2 = resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, query, p_r, count, None, output, p_h, p_big, s))
+
+            def record2(s):
+                for b, e in spans:
+                    if e > b:
+                        p_rays = ctx.tensor_ptr(d_rays[name], 32 * b)
+                        p_hits = peer.ptr(item * b) if peer is not None else ctx.tensor_ptr(local, item * b)
+                        ctx.cmd_intersect(geom.p_nodes, query, p_rays, e - b, None, output, p_hits, p_big, s)
+            go2 = resubmitter(record2)
             ctx.set_option(api.RR_CUDA_OPTION_SORT_RAYS, 0)
             ms2 = timed(go2, steps, 2) / steps
             out["diffuse_binned_ms"] = round(ms2, 4)
