@@ -479,6 +479,35 @@ __device__ __forceinline__ void write_closest(const TraceParams& P, uint32_t gid
     }
 }
 
+// Both slots of a lane against one box: the six plane distances of the two rays come out of six FFMA2, each with the box coordinate
+// as a broadcast scalar operand and the two rays' (inv, -o * inv) packed per axis -- the same fma per ray as slab<kOct>, so the same
+// bits -- instead of 2 FFMA2 + 2 FFMA per ray.
+struct PairConsts
+{
+    uint64_t inv[3], ox[3];   // per axis: (slot 0, slot 1)
+};
+template <int kOct>
+__device__ __forceinline__ void slab_pair(float4 bmin, float4 bmax, const PairConsts& c, const float (&t_max)[2], const float (&t_min)[2],
+                                          float (&t0)[2], float (&t1)[2])
+{
+    float lx[2], ly[2], lz[2], hx[2], hy[2], hz[2];
+    unpack2(fma2(pack2(bmin.x, bmin.x), c.inv[0], c.ox[0]), lx[0], lx[1]);
+    unpack2(fma2(pack2(bmax.x, bmax.x), c.inv[0], c.ox[0]), hx[0], hx[1]);
+    unpack2(fma2(pack2(bmin.y, bmin.y), c.inv[1], c.ox[1]), ly[0], ly[1]);
+    unpack2(fma2(pack2(bmax.y, bmax.y), c.inv[1], c.ox[1]), hy[0], hy[1]);
+    unpack2(fma2(pack2(bmin.z, bmin.z), c.inv[2], c.ox[2]), lz[0], lz[1]);
+    unpack2(fma2(pack2(bmax.z, bmax.z), c.inv[2], c.ox[2]), hz[0], hz[1]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+    {
+        const float ax = (kOct & 1) ? lx[k] : hx[k], ix = (kOct & 1) ? hx[k] : lx[k];
+        const float ay = (kOct & 2) ? ly[k] : hy[k], iy = (kOct & 2) ? hy[k] : ly[k];
+        const float az = (kOct & 4) ? lz[k] : hz[k], iz = (kOct & 4) ? hz[k] : lz[k];
+        t1[k] = fminf(fminf(az, fminf(ax, ay)), t_max[k]);
+        t0[k] = fmaxf(fmaxf(iz, fmaxf(ix, iy)), t_min[k]);
+    }
+}
+
 // One packet, start to finish.  Returns false when the shared stack overflowed (nothing has been written then).
 // The loop is written for issue slots (the kernel is issue bound, profiles/round2_summary.md): both slots are tested at every
 // node (their arithmetic interleaves), a lane without a ray carries closest = -FLT_MAX so that no test of it can pass, one
@@ -496,6 +525,11 @@ __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stac
     const uint32_t stack_hi = stack_lo + kPacketStack * 4;
     uint32_t cur = kTop ? kTopTag : 0u;  // the root (slot 0 of the staged top when kTop)
     const bool lane0 = (threadIdx.x & 31) == 0;
+    PairConsts pc;
+    pc.inv[0] = pack2(ray[0].inv.x, ray[1].inv.x); pc.inv[1] = pack2(ray[0].inv.y, ray[1].inv.y); pc.inv[2] = pack2(ray[0].inv.z, ray[1].inv.z);
+    pc.ox[0] = pack2(ray[0].oxinv.x, ray[1].oxinv.x); pc.ox[1] = pack2(ray[0].oxinv.y, ray[1].oxinv.y); pc.ox[2] = pack2(ray[0].oxinv.z, ray[1].oxinv.z);
+    const float min_t[2] = {r0[0].w, r0[1].w};
+
     while (true)
     {
         float4 q0, q1, q2, q3;
@@ -512,14 +546,12 @@ __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stac
         }
         if (wbits(q0) != kInvalid)
         {
-            float a0, a1, b0, b1, c0, c1, d0, d1;
-            slab<kOct>(q0, q1, ray[0], closest[0], r0[0].w, a0, a1);
-            slab<kOct>(q2, q3, ray[0], closest[0], r0[0].w, b0, b1);
-            slab<kOct>(q0, q1, ray[1], closest[1], r0[1].w, c0, c1);
-            slab<kOct>(q2, q3, ray[1], closest[1], r0[1].w, d0, d1);
-            const bool     any0  = __any_sync(0xffffffffu, a0 <= a1 || c0 <= c1);
-            const bool     any1  = __any_sync(0xffffffffu, b0 <= b1 || d0 <= d1);
-            const bool     first1 = __popc(__ballot_sync(0xffffffffu, b0 < a0)) > 16;  // majority of the slot-0 rays: child 1 is nearer
+            float e0[2], e1[2], f0[2], f1[2];   // child 0: [e0, e1], child 1: [f0, f1], per slot
+            slab_pair<kOct>(q0, q1, pc, closest, min_t, e0, e1);
+            slab_pair<kOct>(q2, q3, pc, closest, min_t, f0, f1);
+            const bool     any0  = __any_sync(0xffffffffu, e0[0] <= e1[0] || e0[1] <= e1[1]);
+            const bool     any1  = __any_sync(0xffffffffu, f0[0] <= f1[0] || f0[1] <= f1[1]);
+            const bool     first1 = __popc(__ballot_sync(0xffffffffu, f0[0] < e0[0])) > 16;  // majority of the slot-0 rays: child 1 is nearer
             const bool     take1 = any1 && (!any0 || first1);
             if (any0 && any1)
             {   // defer the other child: one predicated store each instead of a select (the kernel is bound by the ALU pipe)
