@@ -551,7 +551,9 @@ __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stac
             slab_pair<kOct>(q2, q3, pc, closest, min_t, f0, f1);
             const bool     any0  = __any_sync(0xffffffffu, e0[0] <= e1[0] || e0[1] <= e1[1]);
             const bool     any1  = __any_sync(0xffffffffu, f0[0] <= f1[0] || f0[1] <= f1[1]);
-            const bool     first1 = __popc(__ballot_sync(0xffffffffu, f0[0] < e0[0])) > 16;  // majority of the slot-0 rays: child 1 is nearer
+            // child 1 first when it is the nearer one for any slot-0 ray (a majority vote over the rays visits 0.3 % fewer nodes in the
+            // CPU model of the walk, and costs a POPC and two compares more per node)
+            const bool     first1 = __any_sync(0xffffffffu, f0[0] < e0[0]);
             const bool     take1 = any1 && (!any0 || first1);
             if (any0 && any1)
             {   // defer the other child: one predicated store each instead of a select (the kernel is bound by the ALU pipe)
