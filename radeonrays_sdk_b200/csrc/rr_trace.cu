@@ -1,12 +1,16 @@
 // rr_trace.cu -- closest-hit / any-hit BVH2 traversal, one level (geometry) and two level (scene).
 //
-// Restates vlk/kernels/isect.comp:88-246 and isect_2l.comp:105-323 (+ common.h:103-209): one ray per
-// thread, while-while traversal, near child first (`c1first = hit1 && t0_0 > t0_1`), the other child
-// deferred on a LIFO stack, slab test with explicit fma, Moller-Trumbore with the shader's evaluation
-// order (library is built with --fmad=false so nothing else is contracted).  The visit order is the
-// reference's, which is what makes ANY-hit ids and closest-hit ties reproducible.
+// Two traversal kernels share the reference's arithmetic (slab test with explicit fma, Moller-Trumbore with the shader's
+// evaluation order; the library is built with --fmad=false so nothing else is contracted):
 //
-// B200 mapping:
+//  * k_trace -- restates vlk/kernels/isect.comp:88-246 and isect_2l.comp:105-323 (+ common.h:103-209): one ray per thread,
+//    near child first (`c1first = hit1 && t0_0 > t0_1`), the other child deferred on a LIFO stack.  The visit order is the
+//    reference's, which is what makes ANY-hit ids and first-found closest hits reproducible: it serves ANY queries, everything
+//    two-level, RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, and whatever the packet kernel declines.
+//  * k_trace_packet -- closest hits under the default (t, prim) rule for coherent rays: 64 rays per warp share ONE walk
+//    (see the comment above it).  6.05 -> 7.24 Grays/s on the C2 batch.
+//
+// B200 mapping of k_trace:
 //  * persistent CTAs (a multiple of the SM count); each warp pulls 32-ray chunks from a ticket, so per-thread state
 //    is bounded by resident threads, not by ray_count (the reference asks for 256 B of global stack per ray: 4 GiB
 //    for a 16 Mi batch, vlk/geometry_trace.cpp:169);
@@ -18,9 +22,9 @@
 //    direction octant, a loop specialised for that octant in which min/max(far,near) per axis is a compile-time
 //    choice (bit-identical, see slab<>): 8 FMA-pipe + 8 min/max instructions instead of 12 + 20.
 // Roofline: compulsory HBM traffic is 32 B/ray in + 16 B (or 4 B) out and the BVH is L2 resident, so HBM is not the
-// bound.  Every lane pulls the 64 bytes of each node it visits through the SM's 128 B/clk L1 data path: 2 node visits
-// per clock per SM, i.e. ~8.7 Grays/s for Sponza primary rays (60.5 visits/ray) before any instruction is counted;
-// issue slots are the second limit (profiles/).
+// bound.  In k_trace every lane pulls the 64 bytes of each node it visits through the SM's L1 return path (4 bytes per lane
+// per clock per SM whatever the address pattern, tools/ubench/l1_broadcast.cu): 91 % busy on the C2 batch; k_trace_packet halves
+// the bytes per ray by sharing the visit and is bound by issue slots / the ALU pipe (profiles/).
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
