@@ -143,13 +143,13 @@ __global__ void __launch_bounds__(kTreeletWarps * 32)
             internal_nodes[0]  = node;
             internal_update[0] = wbits(q3);
             root_parent        = wbits(q2);
-            if (lane == 0) my_leaf = wbits(q0);
-            if (lane == 1) my_leaf = wbits(q1);
-            if (lane < 2)
-            {
-                treelet_node_box(nodes, my_leaf, leaf0, my_lo, my_hi);
-                my_area = box_area(my_lo, my_hi);
-            }
+            // A node stores the boxes of its two children, and they are bit-equal to what GetNodeAabb (restructure_bvh.comp:71-88)
+            // computes from the child itself -- the union of the child's own two stored boxes, or of its three vertices; min / max
+            // are exact -- so the box of a new treelet leaf comes from the node just fetched instead of a second, dependent load
+            // of the child (two L2 round trips per growth step were ~40 % of a treelet's latency, and the climb is serial).
+            if (lane == 0) { my_leaf = wbits(q0); my_lo = xyz(q0); my_hi = xyz(q1); }
+            if (lane == 1) { my_leaf = wbits(q1); my_lo = xyz(q2); my_hi = xyz(q3); }
+            if (lane < 2) my_area = box_area(my_lo, my_hi);
         }
         for (int size = 2; size < 7; ++size)
         {
@@ -162,16 +162,12 @@ __global__ void __launch_bounds__(kTreeletWarps * 32)
                 if (li < leaf0 && (largest == 0.0f || ai > largest)) { largest = ai; pick = li; slot = i; }
             }
             const float4* pp = reinterpret_cast<const float4*>(nodes + pick);
-            const float4  q0 = __ldcg(pp), q1 = __ldcg(pp + 1), q3 = __ldcg(pp + 3);
+            const float4  q0 = __ldcg(pp), q1 = __ldcg(pp + 1), q2 = __ldcg(pp + 2), q3 = __ldcg(pp + 3);
             internal_nodes[size - 1]  = pick;
             internal_update[size - 1] = wbits(q3);
-            if (lane == (int)slot) my_leaf = wbits(q0);
-            if (lane == size) my_leaf = wbits(q1);
-            if (lane == (int)slot || lane == size)
-            {
-                treelet_node_box(nodes, my_leaf, leaf0, my_lo, my_hi);
-                my_area = box_area(my_lo, my_hi);
-            }
+            if (lane == (int)slot) { my_leaf = wbits(q0); my_lo = xyz(q0); my_hi = xyz(q1); }
+            if (lane == size) { my_leaf = wbits(q1); my_lo = xyz(q2); my_hi = xyz(q3); }
+            if (lane == (int)slot || lane == size) my_area = box_area(my_lo, my_hi);
         }
         if (lane < 7) { S.lo[lane] = my_lo; S.hi[lane] = my_hi; }
         __syncwarp();
