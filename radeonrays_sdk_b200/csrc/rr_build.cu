@@ -670,7 +670,9 @@ __global__ void __launch_bounds__(32 * kWindowWarps, 5) k_emit_window(EmitParams
     for (int k = lane; k < cnt + 1; k += 32)
     {
         const int a = b0 - 1 + k;
-        delta[k] = (uint8_t)((a >= 0 && a + 1 < n) ? (p.from_tail ? (int)p.deltas[a] : delta_of(p.codes[a], p.codes[a + 1], a)) : 0);
+        // (a mesh build has just written delta(j, j+1) of every leaf into the geometry buffer's tail, k_emit_leaves: one byte to read
+        // here instead of two codes -- this loop was 19 % of the kernel's stall samples; scene builds keep no deltas)
+        delta[k] = (uint8_t)((a >= 0 && a + 1 < n) ? (p.deltas ? (int)p.deltas[a] : delta_of(p.codes[a], p.codes[a + 1], a)) : 0);
     }
     auto delta_adj = [&](int a) -> int { return (int)delta[a + 1 - b0]; };   // a in [b0-1, b1]
     const int ngrp = (cnt + 31) >> 5;
@@ -814,7 +816,7 @@ __global__ void __launch_bounds__(32 * kUpperWarps) k_emit_upper(EmitParams p, c
     __syncthreads();
 
     auto delta_at = [&](int a) -> int {
-        return (a >= 0 && a + 1 < n) ? (p.from_tail ? (int)p.deltas[a] : delta_of(p.codes[a], p.codes[a + 1], a)) : 0;
+        return (a >= 0 && a + 1 < n) ? (p.deltas ? (int)p.deltas[a] : delta_of(p.codes[a], p.codes[a + 1], a)) : 0;
     };
     auto direct_store = [&](uint32_t idx, float4 q0, float4 q1, float4 q2, float4 q3) { st_node(p.nodes + idx, q0, q1, q2, q3); };
     bool prev_formed = true;
