@@ -656,7 +656,7 @@ constexpr int kWindowWarps = 8;  // per CTA
 template <bool kScene>
 __global__ void __launch_bounds__(32 * kWindowWarps, 5) k_emit_window(EmitParams p)
 {
-    __shared__ uint8_t  s_delta[kWindowWarps][kEmitWindow + 8];  // delta(a, a+1) for a = b0-1 .. b1
+    __shared__ __align__(16) uint8_t s_delta[kWindowWarps][kEmitWindow + 16];  // delta(a, a+1) for a = b0-4 .. b0+515: byte a - (b0 - 4)
     __shared__ uint32_t s_mask[kWindowWarps][2][kEmitWindow / 32];
     __shared__ uint16_t s_list[kWindowWarps][kEmitWindow + 2];  // left ends (relative to b0) of the current elements, ascending
     const uint32_t full = 0xffffffffu;
@@ -667,14 +667,23 @@ __global__ void __launch_bounds__(32 * kWindowWarps, 5) k_emit_window(EmitParams
     if (p.from_tail && *p.karras != 1u) return;  // restructured tree: the generic refit kernels do the work
     const int cnt = min(kEmitWindow, n - b0), b1 = b0 + cnt - 1;
     uint8_t*  delta = s_delta[wi];
-    for (int k = lane; k < cnt + 1; k += 32)
-    {
-        const int a = b0 - 1 + k;
-        // (a mesh build has just written delta(j, j+1) of every leaf into the geometry buffer's tail, k_emit_leaves: one byte to read
-        // here instead of two codes -- this loop was 19 % of the kernel's stall samples; scene builds keep no deltas)
-        delta[k] = (uint8_t)((a >= 0 && a + 1 < n) ? (p.deltas ? (int)p.deltas[a] : delta_of(p.codes[a], p.codes[a + 1], a)) : 0);
+    if (p.deltas)
+    {   // a mesh build has just written delta(j, j+1) of every leaf into the geometry buffer's tail (k_emit_leaves), a refit finds
+        // them there: the window's 513 bytes come in as 130 aligned words (b0 is a multiple of 512), staged at the same alignment.
+        // (Reading two codes per delta here was 19 % of the kernel's stall samples; delta(n-1, n) is stored as 0, the padding of the
+        // tail array is never looked at: delta_adj is only asked for a <= b1.)
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.deltas + b0) - 1;   // word holding delta(b0-4 .. b0-1)
+        uint32_t*       dst = reinterpret_cast<uint32_t*>(delta);
+        const int       words = (cnt + 4 + 3) / 4;                                     // bytes b0-4 .. b1
+        for (int k = lane; k < words; k += 32) dst[k] = (b0 == 0 && k == 0) ? 0u : __ldg(src + k);
     }
-    auto delta_adj = [&](int a) -> int { return (int)delta[a + 1 - b0]; };   // a in [b0-1, b1]
+    else
+        for (int k = lane; k < cnt + 1; k += 32)
+        {
+            const int a = b0 - 1 + k;
+            delta[k + 3] = (uint8_t)((a >= 0 && a + 1 < n) ? delta_of(p.codes[a], p.codes[a + 1], a) : 0);
+        }
+    auto delta_adj = [&](int a) -> int { return (int)delta[a + 4 - b0]; };   // a in [b0-1, b1]
     const int ngrp = (cnt + 31) >> 5;
     if (lane < kEmitWindow / 32) s_mask[wi][0][lane] = lane < ngrp ? p.masks[(b0 >> 5) + lane] : 0u;
     __syncwarp();
