@@ -415,7 +415,8 @@ __device__ __forceinline__ MergeOut group_merge(StoreNode&& store_node, int n, i
         lane_range_reduce<false>(hi.y, lane, lenL, pr, lenR, hiL.y, hiR.y);
         lane_range_reduce<false>(hi.z, lane, lenL, pr, lenR, hiL.z, hiR.z);
     }
-    if (formed) store_node(idx, pack(loL, c0), pack(hiL, c1), pack(loR, parent_in ? pidx : kInvalid), pack(hiR, 0u));
+    if (formed)
+        store_node(idx, pack(loL, c0), pack(hiL, c1), pack(loR, parent_in ? pidx : kInvalid), pack(hiR, node_update_word(c0, c1, (uint32_t)n - 1u, 0u)));
 
     // the elements themselves: parent = the node split at the larger of the two neighbouring deltas
     int Dprev = __shfl_up_sync(full, D, 1);
@@ -905,7 +906,8 @@ __global__ void __launch_bounds__(32 * kUpperWarps) k_emit_upper(EmitParams p, c
 
 // ---- K6: refit / update (lbvh_fit_aabb_mesh.comp with UPDATE_KERNEL, vlk/update_hlbvh.cpp:118-185) ----
 // Topology untouched (it may be a treelet-restructured tree, so nothing is assumed about node numbering).  The
-// rendezvous counter is the node's own `update` word used as a parity bit (atomicAdd; even = first arrival), so no
+// rendezvous counter is bit 0 of the node's own `update` word used as a parity bit (atomicXor; even = first arrival; the
+// other bits are the builder's leaf flags, rr_internal.h node_update_word), so no
 // reset pass is needed -- the reference's reset kernel covers only the first 1024 primitives.
 //
 // Three stages.  A thread that is still climbing after `max_levels` parents appends the node it just finished to a
@@ -928,7 +930,7 @@ __device__ __forceinline__ void refit_climb_in_place(Node* __restrict__ nodes, i
     while (parent != kInvalid)
     {
         __threadfence();
-        const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(nodes + parent) + 15, 1u);
+        const uint32_t old = atomicXor(reinterpret_cast<uint32_t*>(nodes + parent) + 15, 1u);
         if ((old & 1u) == 0) break;
         __threadfence();
         float4* pp = reinterpret_cast<float4*>(nodes + parent);
@@ -1014,7 +1016,7 @@ __global__ void __launch_bounds__(256)
                     break;
                 }
                 __threadfence();
-                const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(nodes + parent) + 15, 1u);
+                const uint32_t old = atomicXor(reinterpret_cast<uint32_t*>(nodes + parent) + 15, 1u);
                 if ((old & 1u) == 0) break;
                 __threadfence();
                 float4* pp = reinterpret_cast<float4*>(nodes + parent);

@@ -29,6 +29,16 @@ constexpr uint32_t kSentinel = 0xFFFFFFFEu;  // isect_2l.comp RR_TOP_LEVEL_SENTI
 // bits of DeviceInfo::error_word
 constexpr uint32_t kErrorTraceStackOverflow = 1u, kErrorEmitListOverflow = 2u;
 
+// The `update` word of an internal node (VkBvhNode::update, refit scratch state in the reference and not part of the node parity)
+// carries what the packet traversal wants to know before it fetches a child: bits 1 / 2 = child0 / child1 is a leaf, bit 0 = the
+// refit's rendezvous parity (toggled with atomicXor), bits 31..8 = a tag that says "written by this builder" -- a node array
+// that comes from elsewhere (a dump of the reference's) has small counters there and is traced by the per-ray kernel.
+constexpr uint32_t kNodeTag = 0x52A5C300u, kNodeTagMask = 0xFFFFFF00u, kNodeLeaf0 = 2u, kNodeLeaf1 = 4u;
+__host__ __device__ inline uint32_t node_update_word(uint32_t child0, uint32_t child1, uint32_t first_leaf, uint32_t parity)
+{
+    return kNodeTag | (child0 >= first_leaf ? kNodeLeaf0 : 0u) | (child1 >= first_leaf ? kNodeLeaf1 : 0u) | (parity & 1u);
+}
+
 // 64-byte BVH2 node, identical to the reference's layout (vlk/kernels/bvh2.h:25-35) so that a raw
 // dump of a geometry buffer is a VkBvhNode[] that bvh_analyzer can load (bvh_analyzer/transform.h:31-41).
 //   q0 = (aabb0_min | v0, child0)   q1 = (aabb0_max | v1, child1)

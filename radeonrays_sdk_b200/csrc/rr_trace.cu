@@ -453,28 +453,26 @@ __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(Tra
 // ANY queries and RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND depend on the reference's visit order and stay on k_trace.
 // A packet whose 64 rays do not share a direction octant, or whose shared stack would overflow, is handed to k_trace through
 // the chunk list (two 32-ray chunks), which then runs in list mode right after this kernel.
-constexpr int      kTopLevels = 8;             // (experiment variant of k_trace_packet: levels of the tree staged in shared memory)
-constexpr int      kTopNodes  = (1 << kTopLevels) - 1;
-constexpr uint32_t kTopTag    = 0x80000000u;
 constexpr int      kPacketThreads = 128;
 constexpr int      kPacketStack   = 64;            // entries per warp; LBVH depth beyond that goes to k_trace / k_trace_deep
 
 template <bool kFullHit>
 __device__ __forceinline__ void write_closest(const TraceParams& P, uint32_t gidx, const float4& r0, const float4& r1, float closest,
-                                              uint32_t closest_addr, uint32_t closest_prim)
-{
+                                              uint32_t closest_addr)
+{   // the primitive id is word 7 of the leaf (the traversal keeps only the leaf's address: registers)
     if (closest_addr != kInvalid)
     {
+        const float4* np = reinterpret_cast<const float4*>(P.bvh + closest_addr);
         if (kFullHit)
         {
             RayState ray;
             ray.o = v3(r0); ray.d = v3(r1);
-            const float4* np = reinterpret_cast<const float4*>(P.bvh + closest_addr);
-            const float2  uv = barycentrics(ray, closest, __ldg(np), __ldg(np + 1), __ldg(np + 2));
-            __stcs(reinterpret_cast<float4*>(P.hits) + gidx, make_float4(uv.x, uv.y, __uint_as_float(0u), __uint_as_float(closest_prim)));
+            const float4 l1 = __ldg(np + 1);
+            const float2 uv = barycentrics(ray, closest, __ldg(np), l1, __ldg(np + 2));
+            __stcs(reinterpret_cast<float4*>(P.hits) + gidx, make_float4(uv.x, uv.y, __uint_as_float(0u), l1.w));
         }
         else
-            __stcs(reinterpret_cast<uint32_t*>(P.hits) + gidx, closest_prim);
+            __stcs(reinterpret_cast<uint32_t*>(P.hits) + gidx, __ldg(reinterpret_cast<const uint32_t*>(np) + 7));
     }
     else
     {   // miss: only the id word is written (isect.comp:238-245)
@@ -486,6 +484,14 @@ __device__ __forceinline__ void write_closest(const TraceParams& P, uint32_t gid
 // Both slots of a lane against one box: the six plane distances of the two rays come out of six FFMA2, each with the box coordinate
 // as a broadcast scalar operand and the two rays' (inv, -o * inv) packed per axis -- the same fma per ray as slab<kOct>, so the same
 // bits -- instead of 2 FFMA2 + 2 FFMA per ray.
+// One lane of the (converged) warp: ELECT instead of reading the lane id and comparing.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t p;
+    asm volatile("{ .reg .pred e; elect.sync _|e, 0xffffffff; selp.u32 %0, 1, 0, e; }" : "=r"(p));
+    return p != 0;
+}
+
 struct PairConsts
 {
     uint64_t inv[3], ox[3];   // per axis: (slot 0, slot 1)
@@ -514,21 +520,24 @@ __device__ __forceinline__ void slab_pair(float4 bmin, float4 bmax, const PairCo
 
 // One packet, start to finish.  Returns false when the shared stack overflowed (nothing has been written then).
 // The loop is written for issue slots (the kernel is issue bound, profiles/round2_summary.md): both slots are tested at every
-// node (their arithmetic interleaves), a lane without a ray carries closest = -FLT_MAX so that no test of it can pass, one
-// predicate per child ("any of my two rays wants it") feeds one VOTE.ANY, the near child is the one most lanes' slot-0 rays
-// enter first, and the stack is addressed through a 32-bit shared-memory address.
-template <bool kFullHit, int kOct, bool kTop>
-__device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stack_lo, const uint32_t (&gidx)[2], const bool (&valid)[2],
-                                             const float4 (&r0)[2], const float4 (&r1)[2], const RayState (&ray)[2], const float4* s_top,
-                                             const uint32_t* s_top_id)
+// internal node (their arithmetic interleaves), a lane without a ray carries closest = -FLT_MAX so that no test of it can pass,
+// one predicate per child ("any of my two rays wants it") feeds one VOTE.ANY, the near child is the one some slot-0 ray enters
+// first, and the stack is addressed through a 32-bit shared-memory address.
+// Leaves are never visited as nodes of their own: the builder marks in an internal node's `update` word which of its children are
+// leaves (rr_internal.h node_update_word), and a leaf child is tested right where its box was -- its triangle is fetched only when
+// some ray's box test passed, and only the slots that have such a ray run the Moeller-Trumbore test (a leaf's box is small: 60 %
+// of the leaf visits of the C2 batch concern one of the two 32-ray slots only).  `cur` and the stack hold internal nodes only.
+template <bool kFullHit, int kOct>
+__device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stack_lo, uint32_t gidx0, const bool (&valid)[2],
+                                             const float4 (&r0)[2], const float4 (&r1)[2], const RayState (&ray)[2])
 {
     const float kNever = -3.402823466e+38f;
     float    closest[2]      = {valid[0] ? r1[0].w : kNever, valid[1] ? r1[1].w : kNever};
-    uint32_t closest_addr[2] = {kInvalid, kInvalid}, closest_prim[2] = {kInvalid, kInvalid};
-    uint32_t sp  = stack_lo;                                   // shared-memory byte address of the next free entry
-    const uint32_t stack_hi = stack_lo + kPacketStack * 4;
-    uint32_t cur = kTop ? kTopTag : 0u;  // the root (slot 0 of the staged top when kTop)
-    const bool lane0 = (threadIdx.x & 31) == 0;
+    uint32_t closest_addr[2] = {kInvalid, kInvalid};             // the leaf of the closest hit so far
+    // shared-memory byte address of the next free entry; a warp's stack is the first 256 bytes of a 512-byte aligned block, so
+    // "empty" and "full" are bit tests on the pointer (no bounds held in registers)
+    uint32_t sp  = stack_lo;
+    uint32_t cur = 0u;                                         // the root: an internal node (k_trace_packet checked)
     PairConsts pc;
     pc.inv[0] = pack2(ray[0].inv.x, ray[1].inv.x); pc.inv[1] = pack2(ray[0].inv.y, ray[1].inv.y); pc.inv[2] = pack2(ray[0].inv.z, ray[1].inv.z);
     pc.ox[0] = pack2(ray[0].oxinv.x, ray[1].oxinv.x); pc.ox[1] = pack2(ray[0].oxinv.y, ray[1].oxinv.y); pc.ox[2] = pack2(ray[0].oxinv.z, ray[1].oxinv.z);
@@ -537,22 +546,15 @@ __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stac
     while (true)
     {
         float4 q0, q1, q2, q3;
-        if (kTop && (cur & kTopTag))
-        {   // experiment: the top levels of the tree staged in shared memory (see k_trace_packet)
-            const float4* sp = s_top + 4 * (cur & ~kTopTag);
-            q0 = sp[0]; q1 = sp[1]; q2 = sp[2]; q3 = sp[3];
-        }
-        else
-        {
-            const float4* np = reinterpret_cast<const float4*>(P.bvh + cur);
-            ldg_half_node(np, q0, q1);
-            ldg_half_node(np + 2, q2, q3);
-        }
-        if (wbits(q0) != kInvalid)
-        {
-            float e0[2], e1[2], f0[2], f1[2];   // child 0: [e0, e1], child 1: [f0, f1], per slot
-            slab_pair<kOct>(q0, q1, pc, closest, min_t, e0, e1);
-            slab_pair<kOct>(q2, q3, pc, closest, min_t, f0, f1);
+        const float4* np = reinterpret_cast<const float4*>(P.bvh + cur);
+        ldg_half_node(np, q0, q1);
+        ldg_half_node(np + 2, q2, q3);
+        float e0[2], e1[2], f0[2], f1[2];   // child 0: [e0, e1], child 1: [f0, f1], per slot
+        slab_pair<kOct>(q0, q1, pc, closest, min_t, e0, e1);
+        slab_pair<kOct>(q2, q3, pc, closest, min_t, f0, f1);
+        const uint32_t tag = wbits(q3);
+        if ((tag & (kNodeLeaf0 | kNodeLeaf1)) == 0)
+        {   // two internal children
             const bool     any0  = __any_sync(0xffffffffu, e0[0] <= e1[0] || e0[1] <= e1[1]);
             const bool     any1  = __any_sync(0xffffffffu, f0[0] <= f1[0] || f0[1] <= f1[1]);
             // child 1 first when it is the nearer one for any slot-0 ray (a majority vote over the rays visits 0.3 % fewer nodes in the
@@ -561,9 +563,9 @@ __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stac
             const bool     take1 = any1 && (!any0 || first1);
             if (any0 && any1)
             {   // defer the other child: one predicated store each instead of a select (the kernel is bound by the ALU pipe)
-                if (sp >= stack_hi) return false;
+                if (sp & (kPacketStack * 4)) return false;
                 __syncwarp();  // every lane's earlier pop of this slot has completed
-                if (lane0)
+                if (elect_one())
                 {   // one lane writes the warp's stack; the barrier below orders the store before any lane's later pop
                     if (take1) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(wbits(q0)) : "memory");
                     else       asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(wbits(q1)) : "memory");
@@ -578,77 +580,85 @@ __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stac
             }
         }
         else
-        {
-            const uint32_t prim = wbits(q1);
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
+        {   // at least one leaf child: test it here; at most one internal child is left to descend into, nothing to defer.
+            // Written so that one register (`other`) and two predicates survive a triangle test: the second child, leaf or not.
+            const bool leaf0 = (tag & kNodeLeaf0) != 0, both = (tag & (kNodeLeaf0 | kNodeLeaf1)) == (kNodeLeaf0 | kNodeLeaf1);
+            uint32_t leaf, other;
+            bool     want0, want1, other0, other1;
+            if (leaf0)
+            {   // (a uniform branch instead of selects between predicates: those cost ~20 instructions)
+                leaf = wbits(q0); other = wbits(q1);
+                want0  = __any_sync(0xffffffffu, e0[0] <= e1[0]); want1  = __any_sync(0xffffffffu, e0[1] <= e1[1]);
+                other0 = __any_sync(0xffffffffu, f0[0] <= f1[0]); other1 = __any_sync(0xffffffffu, f0[1] <= f1[1]);
+            }
+            else
             {
-                float t;
-                if (tri_test(ray[k], r0[k].w, q0, q1, q2, closest[k], t) && (t < closest[k] || (closest_addr[k] != kInvalid && prim < closest_prim[k])))
-                {   // tri_test accepted t <= closest: smaller t, or the same t and a lower primitive id
-                    closest[k]      = t;
-                    closest_addr[k] = cur;
-                    closest_prim[k] = prim;
+                leaf = wbits(q1); other = wbits(q0);
+                want0  = __any_sync(0xffffffffu, f0[0] <= f1[0]); want1  = __any_sync(0xffffffffu, f0[1] <= f1[1]);
+                other0 = __any_sync(0xffffffffu, e0[0] <= e1[0]); other1 = __any_sync(0xffffffffu, e0[1] <= e1[1]);
+            }
+            bool again = both;
+            while (true)
+            {
+                if (want0 || want1)
+                {
+                    const float4*  lp = reinterpret_cast<const float4*>(P.bvh + leaf);
+                    float4 l0, l1;
+                    ldg_half_node(lp, l0, l1);
+                    const float4   l2 = __ldg(lp + 2);
+                    const uint32_t prim = wbits(l1);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                    {
+                        if (k == 0 ? want0 : want1)
+                        {
+                            float t;
+                            if (tri_test(ray[k], min_t[k], l0, l1, l2, closest[k], t) &&
+                                (t < closest[k] || (closest_addr[k] != kInvalid && prim < __ldg(reinterpret_cast<const uint32_t*>(P.bvh + closest_addr[k]) + 7))))
+                            {   // tri_test accepted t <= closest: smaller t, or the same t and a lower primitive id (fetched from the
+                                // leaf of the hit so far in that rare case)
+                                closest[k]      = t;
+                                closest_addr[k] = leaf;
+                            }
+                        }
+                    }
                 }
+                if (!again) break;
+                again = false;
+                leaf = other; want0 = other0; want1 = other1;
+            }
+            if (!both && (other0 || other1))
+            {   // the internal sibling (decided with the closest hits as they were when its box was tested)
+                cur = other;
+                continue;
             }
         }
-        if (sp == stack_lo) break;
+        if ((sp & (2 * kPacketStack * 4 - 1)) == 0) break;
         sp -= 4;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(sp) : "memory");
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k)
-    {
-        if (kTop && closest_addr[k] != kInvalid && (closest_addr[k] & kTopTag)) closest_addr[k] = s_top_id[closest_addr[k] & ~kTopTag];
-        if (valid[k]) write_closest<kFullHit>(P, gidx[k], r0[k], r1[k], closest[k], closest_addr[k], closest_prim[k]);
-    }
+        if (valid[k]) write_closest<kFullHit>(P, gidx0 + 32 * k, r0[k], r1[k], closest[k], closest_addr[k]);
     return true;
 }
 
-// kTop (experiment, RR_CUDA_PACKET_TOP_LEVELS=1; north_star: "staging of top BVH levels"): every CTA first copies the top
-// kTopLevels levels of the tree (255 nodes, 16 KB) into shared memory in heap order -- slot s holds a node, its children sit in
-// slots 2s+1 / 2s+2 and the staged child words are rewritten to tagged slot numbers -- and the traversal reads tagged nodes with
-// LDS instead of LDG.  Measured on C2 (profiles/round2_summary.md): slower than the plain kernel; the top of the tree is the part
-// that always hits in L1 anyway, an L1 hit costs 32 clk against 29 for LDS, the 16 KB per CTA come out of the L1 capacity the
-// lower levels need, and the tag test adds instructions to a loop that is bound by issue slots.  Off by default.
-template <bool kFullHit, bool kTop>
+// (Round 2 also measured this kernel with the top 8 levels of the tree staged in shared memory per CTA -- BASELINE's "staging of top
+// BVH levels": 6 492 against 6 970 Mrays/s on C2, profiles/round2_summary.md; the top of the tree is the part that always hits in L1
+// anyway, and the tag test adds instructions to a loop that is bound by issue slots.  The variant is in the history, not here.)
+template <bool kFullHit>
 __global__ void __launch_bounds__(kPacketThreads, 8) k_trace_packet(TraceParams P)
 {
-    __shared__ uint32_t s_stack[(kPacketThreads / 32) * kPacketStack];
-    extern __shared__ float4 s_dyn[];
-    float4*   s_top    = s_dyn;
-    uint32_t* s_top_id = reinterpret_cast<uint32_t*>(s_dyn + 4 * kTopNodes);
+    __shared__ __align__(2 * kPacketStack * 4) uint32_t s_stack[(kPacketThreads / 32) * 2 * kPacketStack];
     if (!resolve_scene<false>(P)) return;
-    if (kTop)
-    {
-        for (int i = threadIdx.x; i < kTopNodes; i += kPacketThreads) s_top_id[i] = i == 0 ? 0u : kInvalid;
-        __syncthreads();
-        for (int level = 0; level < kTopLevels; ++level)
-        {
-            const int first = (1 << level) - 1, width = 1 << level;
-            for (int i = threadIdx.x; i < width; i += kPacketThreads)
-            {
-                const int      slot = first + i;
-                const uint32_t id   = s_top_id[slot];
-                if (id == kInvalid) continue;
-                const float4* np = reinterpret_cast<const float4*>(P.bvh + id);
-                float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
-                if (wbits(q0) != kInvalid && level + 1 < kTopLevels)
-                {
-                    s_top_id[2 * slot + 1] = wbits(q0);
-                    s_top_id[2 * slot + 2] = wbits(q1);
-                    q0.w = __uint_as_float(kTopTag | (uint32_t)(2 * slot + 1));
-                    q1.w = __uint_as_float(kTopTag | (uint32_t)(2 * slot + 2));
-                }
-                s_top[4 * slot] = q0; s_top[4 * slot + 1] = q1; s_top[4 * slot + 2] = q2; s_top[4 * slot + 3] = q3;
-            }
-            __syncthreads();
-        }
-    }
     uint32_t count = P.ray_count;
     if (P.indirect) count = min(count, __ldg(P.indirect));
     const uint32_t lane  = threadIdx.x & 31;
-    const uint32_t stack = (uint32_t)__cvta_generic_to_shared(s_stack + (threadIdx.x >> 5) * kPacketStack);
+    const uint32_t stack = (uint32_t)__cvta_generic_to_shared(s_stack + (threadIdx.x >> 5) * 2 * kPacketStack);
+    // Packets need the builder's leaf flags and an internal root: a single-triangle geometry, or a node array that was not written
+    // by this library's builder (no tag in the root's update word), goes to the per-ray kernel chunk by chunk.
+    const uint32_t* root_words = reinterpret_cast<const uint32_t*>(P.bvh);
+    const bool packets_ok = __ldg(root_words + 3) != kInvalid && (__ldg(root_words + 15) & kNodeTagMask) == kNodeTag;
     while (true)
     {
         uint32_t packet = 0;
@@ -673,20 +683,20 @@ __global__ void __launch_bounds__(kPacketThreads, 8) k_trace_packet(TraceParams 
         }
         const uint32_t slots    = (uint64_t)packet * 64 + 32 < count ? 3u : 1u;  // the last packet may hold one chunk only
         const int      oct0     = __shfl_sync(0xffffffffu, oct[0], 0);
-        const bool     coherent = oct0 != 8 && __all_sync(0xffffffffu, oct[0] == oct0 && oct[1] == oct0);
+        const bool     coherent = packets_ok && oct0 != 8 && __all_sync(0xffffffffu, oct[0] == oct0 && oct[1] == oct0);
         bool done = false;
         if (coherent)
         {
             switch (oct0)
             {
-            case 0: done = trace_packet<kFullHit, 0, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
-            case 1: done = trace_packet<kFullHit, 1, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
-            case 2: done = trace_packet<kFullHit, 2, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
-            case 3: done = trace_packet<kFullHit, 3, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
-            case 4: done = trace_packet<kFullHit, 4, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
-            case 5: done = trace_packet<kFullHit, 5, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
-            case 6: done = trace_packet<kFullHit, 6, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
-            default: done = trace_packet<kFullHit, 7, kTop>(P, stack, gidx, valid, r0, r1, ray, s_top, s_top_id); break;
+            case 0: done = trace_packet<kFullHit, 0>(P, stack, gidx[0], valid, r0, r1, ray); break;
+            case 1: done = trace_packet<kFullHit, 1>(P, stack, gidx[0], valid, r0, r1, ray); break;
+            case 2: done = trace_packet<kFullHit, 2>(P, stack, gidx[0], valid, r0, r1, ray); break;
+            case 3: done = trace_packet<kFullHit, 3>(P, stack, gidx[0], valid, r0, r1, ray); break;
+            case 4: done = trace_packet<kFullHit, 4>(P, stack, gidx[0], valid, r0, r1, ray); break;
+            case 5: done = trace_packet<kFullHit, 5>(P, stack, gidx[0], valid, r0, r1, ray); break;
+            case 6: done = trace_packet<kFullHit, 6>(P, stack, gidx[0], valid, r0, r1, ray); break;
+            default: done = trace_packet<kFullHit, 7>(P, stack, gidx[0], valid, r0, r1, ray); break;
             }
         }
         if (!done && lane == 0)
@@ -925,15 +935,8 @@ void trace(const DeviceInfo& dev, cudaStream_t s, const TraceArgs& a)
             Q.chunk_list = chunk_list;
             const size_t need = ((size_t)a.ray_count + 2 * kPacketThreads - 1) / (2 * kPacketThreads);
             const int    grid = (int)std::max<size_t>(1, std::min<size_t>(need, (size_t)dev.sm_count * packet_ctas_per_sm()));
-            static const int top_levels = [] { const char* e = std::getenv("RR_CUDA_PACKET_TOP_LEVELS"); return e ? std::atoi(e) : 0; }();
-            if (top_levels)
-            {   // experiment only (see k_trace_packet): root node 0 is staged with tag 0 | slot 0, i.e. cur = kTopTag
-                const size_t smem = kTopNodes * (4 * sizeof(float4) + sizeof(uint32_t));
-                if (full) k_trace_packet<true, true><<<grid, kPacketThreads, smem, s>>>(Q);
-                else      k_trace_packet<false, true><<<grid, kPacketThreads, smem, s>>>(Q);
-            }
-            else if (full) k_trace_packet<true, false><<<grid, kPacketThreads, 0, s>>>(Q);
-            else           k_trace_packet<false, false><<<grid, kPacketThreads, 0, s>>>(Q);
+            if (full) k_trace_packet<true><<<grid, kPacketThreads, 0, s>>>(Q);
+            else      k_trace_packet<false><<<grid, kPacketThreads, 0, s>>>(Q);
             *dev.launches += 1;
         }
         if (any) { if (full) launch<true, true, false>(dev, s, Q); else launch<true, false, false>(dev, s, Q); }
