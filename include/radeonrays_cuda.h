@@ -60,6 +60,12 @@ typedef enum
      * a compiled-out 64-bit delta() (dx/kernels/build_hlbvh_fallback.hlsl:16,95-108); defined by oracle/rr_oracle.c
      * rro_build_blas63.  Set it before rrGetGeometryBuildMemoryRequirements (the temporary build buffer grows). */
     RR_CUDA_OPTION_MORTON_BITS                    = 5,
+    /* Closest-hit packets are 8 x 8 tiles of the ray grid instead of 64 consecutive rays when the batch is an image in row
+     * order (camera rays generated `for y, for x`, as the reference's tests do): 0 (default) = every rrCmdIntersect looks for
+     * the row length on the device (one small kernel: where does the step between consecutive rays turn back?), 1 = never,
+     * W >= 64 = the rows are W rays long, starting at ray 0.  Only the grouping of rays changes, never a hit: every ray keeps its
+     * own (t, prim) minimum and writes it at its own index. */
+    RR_CUDA_OPTION_RAY_GRID_WIDTH                 = 6,
     /* test hook: caps the hand-over lists of the staged refit (0 = library default) so that tests can drive them into overflow */
     RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY      = 3
 } RRCudaOption;

@@ -31,6 +31,7 @@ RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, RR_CUDA_OPTION_REFERENCE_TRANSFORM_
 RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY = 3
 RR_CUDA_OPTION_SORT_RAYS = 4
 RR_CUDA_OPTION_MORTON_BITS = 5
+RR_CUDA_OPTION_RAY_GRID_WIDTH = 6
 
 _vp = C.c_void_p
 

@@ -659,6 +659,10 @@ RRError rrCudaSetOption(RRContext context, RRCudaOption option, int value)
         C(context)->dev.morton63 = value == 63;
         return RR_SUCCESS;
     case RR_CUDA_OPTION_SORT_RAYS: C(context)->dev.sort_rays = value != 0; return RR_SUCCESS;
+    case RR_CUDA_OPTION_RAY_GRID_WIDTH:
+        if (value < 0 || (value > 1 && value < 64)) return RR_ERROR_INVALID_PARAMETER;
+        C(context)->dev.ray_grid_width = (uint32_t)value;
+        return RR_SUCCESS;
     case RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY: C(context)->dev.refit_list_capacity = value > 0 ? (uint32_t)value : 0u; return RR_SUCCESS;
     default: return RR_ERROR_INVALID_PARAMETER;
     }

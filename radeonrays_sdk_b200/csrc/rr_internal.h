@@ -110,6 +110,7 @@ struct DeviceInfo
     uint64_t* launches   = nullptr;  // per-context launch counter (host side)
     bool      morton63   = false;    // RR_CUDA_OPTION_MORTON_BITS = 63: geometry builds use 21 bits per axis (extension)
     bool      sort_rays  = false;    // RR_CUDA_OPTION_SORT_RAYS: bin the rays of every rrCmdIntersect on the device before tracing
+    uint32_t  ray_grid_width = 0;    // RR_CUDA_OPTION_RAY_GRID_WIDTH: 0 = look for the row length of image-ordered rays, 1 = never, W = told
     uint32_t  refit_list_capacity = 0;  // test hook (RR_CUDA_OPTION_DEBUG_REFIT_LIST_CAPACITY): 0 = sized by the library
     uint32_t* error_word = nullptr;  // device-visible (host-mapped) word the kernels OR error bits into; checked by rrWaitEvent
 };

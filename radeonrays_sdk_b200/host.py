@@ -116,6 +116,7 @@ class Engine:
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         n = rays.shape[0]
         b = self.make_ray_buffers(n, output)
+        self.last_ray_buffers = b   # (tests look at the scratch header afterwards)
         b.d_rays[: 32 * n].copy_(_upload(rays, self.device))
         if init_hits is not None:
             b.d_hits[: b.hit_bytes].copy_(_upload(init_hits, self.device))

@@ -250,6 +250,60 @@ def test_ray_binning_option_is_bit_identical(engine, sponza, cornell):
     assert_hits_equal(got, O.trace(g.nodes(), diffuse), what="binned diffuse", mesh=(pos, idx), rays=diffuse)
 
 
+def _grid_words(engine):
+    """Scratch header words 5 / 6 after an rrCmdIntersect: the row length k_detect_grid settled on (0: none) and the phase of row 0."""
+    w = engine.last_ray_buffers.d_scratch[20:28].cpu().numpy().view(np.int32)
+    return int(w[0]), int(w[1])
+
+
+def test_ray_grid_tiles_are_bit_identical(engine, sponza):
+    """Closest-hit packets are 8 x 8 tiles of the ray grid when the batch is an image in row order (k_detect_grid finds the row
+    length on the device; RR_CUDA_OPTION_RAY_GRID_WIDTH).  The grouping must never change a hit: tiles (detected, and told), and
+    64-ray strips return the same bytes -- for widths that are no multiple of 8, a ragged last row, a batch that starts in mid-row
+    (a shard of a frame), a device-side ray count, rows too short or too few to tile, and rays with no grid at all."""
+    pos, idx, _ = sponza
+    g = engine.build_geometry(pos, idx, build_flags=0)
+    ctx = engine.ctx
+    rng = np.random.default_rng(3)
+
+    def run(rays, mode, **kw):
+        ctx.set_option(api.RR_CUDA_OPTION_RAY_GRID_WIDTH, mode)
+        try:
+            return engine.intersect(g, rays, **kw), _grid_words(engine)
+        finally:
+            ctx.set_option(api.RR_CUDA_OPTION_RAY_GRID_WIDTH, 0)
+
+    img = W.sponza_primary_rays(331, 203)                      # 331 = 41 * 8 + 3 columns, 203 = 25 * 8 + 3 rows
+    cases = [("full frame", img, 331, 0, {}),
+             ("ragged last row", img[: 331 * 150 + 77], 331, 0, {}),
+             ("starts in mid-row", img[1000:], 331, -(1000 % 331), {}),
+             ("device-side count", img, 331, 0, {"indirect_count": 331 * 90 + 5}),
+             ("wide and short", W.sponza_primary_rays(1024, 9), 1024, 0, {}),
+             ("seven rows: strips", W.sponza_primary_rays(1024, 7), 0, 0, {}),
+             ("63 columns: strips", W.sponza_primary_rays(63, 200), 0, 0, {}),
+             ("shuffled rows: strips", img[rng.permutation(img.shape[0])], 0, 0, {})]
+    for what, rays, want_w, want_base, kw in cases:
+        strips, (w1, _) = run(rays, 1, **kw)
+        tiles, (w0, b0) = run(rays, 0, **kw)
+        assert w1 == 0 and (w0, b0) == (want_w, want_base), f"{what}: k_detect_grid said W = {w0}, row 0 starts at ray {b0}"
+        assert np.array_equal(strips.view(np.uint8), tiles.view(np.uint8)), f"{what}: tiles and strips differ"
+    # the client may state the row length (then row 0 starts at ray 0); a wrong one only costs coherence
+    strips, _ = run(img, 1)
+    for w in (331, 300, 4096):
+        told, (w0, b0) = run(img, w)
+        assert (w0, b0) == (w if (img.shape[0] + w - 1) // w >= 8 else 0, 0)
+        assert np.array_equal(strips.view(np.uint8), told.view(np.uint8)), f"told W = {w}"
+    assert ctx.lib.rrCudaSetOption(ctx.handle, api.RR_CUDA_OPTION_RAY_GRID_WIDTH, 17) == api.RR_ERROR_INVALID_PARAMETER
+    # tiles against the oracle (the parity tests above run with detection on as well: it is the default)
+    assert_hits_equal(run(img, 0)[0], O.trace(g.nodes(), img), what="tiles", mesh=(pos, idx), rays=img)
+    # jittered camera rays: consecutive steps may turn back anywhere, nothing to tile, same hits
+    jit = img.copy()
+    jit["direction"] += rng.normal(0, 2e-3, jit["direction"].shape).astype(np.float32)
+    a, (w1, _) = run(jit, 1)
+    b, (w0, _) = run(jit, 0)
+    assert w0 == 0 and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
 def test_degenerate_rays_and_triangles(engine, cornell):
     """Edge cases the arithmetic must survive exactly like the oracle: rays with zero / denormal / huge direction components
     (safe_invdir, common.h:166-183), axis-parallel rays, origins on a vertex / edge / face, max_t below min_t, infinite max_t,
