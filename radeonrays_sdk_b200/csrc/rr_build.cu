@@ -232,6 +232,7 @@ struct EmitParams
     uint32_t*       karras;      // tail header word: 1 while the tree is Karras-numbered (cleared by the treelet restructuring)
     bool            from_tail;   // refit: codes == nullptr, deltas / refs come from the tail; run only if *karras == 1
     uint32_t*       error;     // DeviceInfo::error_word (kErrorEmitListOverflow)
+    bool            static_order;  // quality builds: the traversal orders children by the table in the update word (node_update_word)
     bool            prefetch;  // k_emit_window pulls the node images of its first pass into L2 before it merges
     bool            tma;     // k_emit_leaves stages node images in shared memory and stores them with TMA tensor copies
     uint32_t*       masks;             // [ceil(n/32)] per 32 leaves: left ends of the subtrees k_emit_leaves left over
@@ -366,7 +367,7 @@ struct MergeOut
 // writes a formed node.
 template <bool kLeaves, class StoreNode>
 __device__ __forceinline__ MergeOut group_merge(StoreNode&& store_node, int n, int cnt, bool valid, int a, int b, uint32_t id, float3 lo,
-                                                float3 hi, int D, int DL0)
+                                                float3 hi, int D, int DL0, uint32_t order_flag)
 {
     const uint32_t full  = 0xffffffffu;
     const int      lane  = threadIdx.x & 31;
@@ -416,7 +417,7 @@ __device__ __forceinline__ MergeOut group_merge(StoreNode&& store_node, int n, i
         lane_range_reduce<false>(hi.z, lane, lenL, pr, lenR, hiL.z, hiR.z);
     }
     if (formed)
-        store_node(idx, pack(loL, c0), pack(hiL, c1), pack(loR, parent_in ? pidx : kInvalid), pack(hiR, node_update_word(c0, c1, (uint32_t)n - 1u, 0u)));
+        store_node(idx, pack(loL, c0), pack(hiL, c1), pack(loR, parent_in ? pidx : kInvalid), pack(hiR, node_update_word(c0, c1, (uint32_t)n - 1u, 0u, node_order_bits(loL, hiL, loR, hiR) | order_flag)));
 
     // the elements themselves: parent = the node split at the larger of the two neighbouring deltas
     int Dprev = __shfl_up_sync(full, D, 1);
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(256, kLeavesCtasPerSm)
                 p.fwd[3 * (size_t)ref + 1] = make_float4(d.m[4], d.m[5], d.m[6], d.m[7]);
                 p.fwd[3 * (size_t)ref + 2] = make_float4(d.m[8], d.m[9], d.m[10], d.m[11]);
             }
-            const MergeOut o = group_merge<true>(direct_store, n, cnt, valid, j, j, (uint32_t)(leaf0 + j), lo, hi, D, DL0);
+            const MergeOut o = group_merge<true>(direct_store, n, cnt, valid, j, j, (uint32_t)(leaf0 + j), lo, hi, D, DL0, p.static_order ? 0u : kNodeVoteOrder);
             if (valid) st_node(p.nodes + leaf0 + j, pack(lo, kInvalid), pack(hi, ref), pack(lo, o.e_parent), pack(hi, 0u));
             const uint32_t mask = __ballot_sync(full, o.e_over) | __reduce_or_sync(full, o.n_over ? 1u << ((o.n_a - wb) & 31) : 0u);
             if (lane == 0) p.masks[g] = mask;
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__(256, kLeavesCtasPerSm)
                          "f"(tri_c.v0.y), "f"(tri_c.v0.z), "f"(__uint_as_float(kInvalid)), "f"(tri_c.v1.x), "f"(tri_c.v1.y), "f"(tri_c.v1.z),
                          "f"(__uint_as_float(ref_c))
                          : "memory");
-        const MergeOut o = group_merge<true>(staged_store, n, cnt, valid, j, j, (uint32_t)(leaf0 + j), lo, hi, D, DL0);
+        const MergeOut o = group_merge<true>(staged_store, n, cnt, valid, j, j, (uint32_t)(leaf0 + j), lo, hi, D, DL0, p.static_order ? 0u : kNodeVoteOrder);
         if (tma)
         {
             *quad_at(st_leaf, lane, 2) = pack(v2, o.e_parent);
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(32 * kWindowWarps, 5) k_emit_window(EmitParams
                 node_box_ldcg<kScene>(p.nodes, id, leaf0, elo, ehi);
             }
             const int a_first = __shfl_sync(full, a, 0);
-            const MergeOut o = group_merge<false>(direct_store, n, e1 - e0, v, a, b, id, elo, ehi, v ? delta_adj(b) : 0, delta_adj(a_first - 1));
+            const MergeOut o = group_merge<false>(direct_store, n, e1 - e0, v, a, b, id, elo, ehi, v ? delta_adj(b) : 0, delta_adj(a_first - 1), p.static_order ? 0u : kNodeVoteOrder);
             if (v && o.e_parent != kInvalid) reinterpret_cast<uint32_t*>(p.nodes + id)[11] = o.e_parent;  // q2.w
             if (o.e_over) atomicOr(&s_mask[wi][cur ^ 1][(a - b0) >> 5], 1u << ((a - b0) & 31));
             if (o.n_over) atomicOr(&s_mask[wi][cur ^ 1][(o.n_a - b0) >> 5], 1u << ((o.n_a - b0) & 31));
@@ -853,7 +854,7 @@ __global__ void __launch_bounds__(32 * kUpperWarps) k_emit_upper(EmitParams p, c
                 node_box_ldcg<kScene>(p.nodes, id, leaf0, elo, ehi);
             }
             const int a_first = __shfl_sync(full, a, 0);
-            const MergeOut o = group_merge<false>(direct_store, n, e1 - e0, v, a, b, id, elo, ehi, D, delta_at(a_first - 1));
+            const MergeOut o = group_merge<false>(direct_store, n, e1 - e0, v, a, b, id, elo, ehi, D, delta_at(a_first - 1), p.static_order ? 0u : kNodeVoteOrder);
             if (v && o.e_parent != kInvalid) reinterpret_cast<uint32_t*>(p.nodes + id)[11] = o.e_parent;  // q2.w
             const uint32_t EL = __ballot_sync(full, o.e_over), NL = __ballot_sync(full, o.n_over);
             const uint32_t below = (1u << lane) - 1u;
@@ -942,8 +943,9 @@ __device__ __forceinline__ void refit_climb_in_place(Node* __restrict__ nodes, i
         const float4   s0 = __ldcg(sp), s1 = __ldcg(sp + 1), s2 = __ldcg(sp + 2), s3 = __ldcg(sp + 3);
         float3 slo, shi;
         node_box(s0, s1, s2, s3, sib >= (uint32_t)leaf0, slo, shi);
-        if (is_left) { pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up); pp[3] = pack(shi, old + 1u); }
-        else { pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up); pp[3] = pack(hi, old + 1u); }
+        // (the update word: parity as the atomicXor left it, leaf flags as they were, child order for the new boxes)
+        if (is_left) { pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up); pp[3] = pack(shi, node_update_word(c0, c1, (uint32_t)leaf0, old ^ 1u, node_order_bits(lo, hi, slo, shi) | (old & kNodeVoteOrder))); }
+        else { pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up); pp[3] = pack(hi, node_update_word(c0, c1, (uint32_t)leaf0, old ^ 1u, node_order_bits(slo, shi, lo, hi) | (old & kNodeVoteOrder))); }
         lo = min3(lo, slo);
         hi = max3(hi, shi);
         me = parent;
@@ -1030,11 +1032,13 @@ __global__ void __launch_bounds__(256)
                 node_box(s0, s1, s2, s3, sib >= leaf0, slo, shi);
                 if (is_left)
                 {
-                    pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up); pp[3] = pack(shi, old + 1u);
+                    pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up);
+                    pp[3] = pack(shi, node_update_word(c0, c1, leaf0, old ^ 1u, node_order_bits(lo, hi, slo, shi) | (old & kNodeVoteOrder)));
                 }
                 else
                 {
-                    pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up); pp[3] = pack(hi, old + 1u);
+                    pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up);
+                    pp[3] = pack(hi, node_update_word(c0, c1, leaf0, old ^ 1u, node_order_bits(slo, shi, lo, hi) | (old & kNodeVoteOrder)));
                 }
                 lo = min3(lo, slo);
                 hi = max3(hi, shi);
@@ -1194,7 +1198,8 @@ __global__ void __launch_bounds__(256, 4)  // 64 registers; 3 / 5 / 6 CTAs per S
                     const uint32_t c0 = wbits(h0), c1 = wbits(h1), up = wbits(h2), upd = wbits(h3);
                     const bool     first = c0 == cur;  // which of the two is child0
                     st_node(nodes + par, pack(first ? lo : nlo, c0), pack(first ? hi : nhi, c1), pack(first ? nlo : lo, up),
-                            pack(first ? nhi : hi, upd));
+                            pack(first ? nhi : hi, (upd & ~(0xFFu << kNodeOrderShift)) |
+                                                       (first ? node_order_bits(lo, hi, nlo, nhi) : node_order_bits(nlo, nhi, lo, hi))));
                     lo = min3(lo, nlo);
                     hi = max3(hi, nhi);
                     cur = par;
@@ -1295,7 +1300,8 @@ __global__ void __launch_bounds__(256)
                     const uint32_t  c0 = __ldcg(pw + 3), c1 = __ldcg(pw + 7), up = __ldcg(pw + 11), upd = __ldcg(pw + 15);
                     const bool      first = c0 == id;  // which of the two is child0
                     st_node(nodes + par, pack(first ? lo : nlo, c0), pack(first ? hi : nhi, c1), pack(first ? nlo : lo, up),
-                            pack(first ? nhi : hi, upd));
+                            pack(first ? nhi : hi, (upd & ~(0xFFu << kNodeOrderShift)) |
+                                                       (first ? node_order_bits(lo, hi, nlo, nhi) : node_order_bits(nlo, nhi, lo, hi))));
                     lo = min3(lo, nlo);
                     hi = max3(hi, nhi);
                     id = par;
@@ -1657,6 +1663,7 @@ void build_blas(const DeviceInfo& dev, cudaStream_t s, const MeshDesc& mesh, con
     }
     *dev.launches += 1;
     p.refs = sorted_refs; p.n = n; p.nodes = nodes; p.mesh = mesh;
+    p.static_order = restructure && n >= 64;   // (restructure_blas leaves smaller trees alone, and so does a later refit's re-emission)
     p.lists = reinterpret_cast<uint32_t*>(sc + L.lists_off);
     p.masks = reinterpret_cast<uint32_t*>(sc + L.sort_off + L.sort.tmp_vals_off);  // the sort's ping-pong buffer is dead now
     char* geom  = reinterpret_cast<char*>(nodes);

@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(Tra
     SmemStack<kEntries> st;
     st.base = s_stack + threadIdx.x;
     const RayGrid G = load_grid(kList ? P.grid : nullptr, count);
+    if (kList && *P.chunk_count == 0) return;   // (coherent batches: nothing was declined; no ticket traffic for nothing)
     while (true)
     {
         uint32_t chunk = 0;
@@ -587,7 +588,17 @@ __global__ void __launch_bounds__(1024) k_detect_grid(const float4* __restrict__
     else if (count >= kGridMinWidth * kGridMinRows)
     {
         // the step along a row: directions, or origins when the first two directions are equal (parallel rays)
+        if (threadIdx.x == 0) { s_first = s_second = 0xFFFFFFFFu; s_bad = 0; }
+        __syncthreads();
+        const uint32_t limit = min(count - 1, kGridSearch);
         const float4 o0 = __ldg(rays), d0 = __ldg(rays + 1), o1 = __ldg(rays + 2), d1 = __ldg(rays + 3);
+        float4 da[8], db[8];   // round 0's directions are requested together with the first two rays: one round trip
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            const uint32_t i = min(k * 1024 + threadIdx.x, limit - 1);
+            da[k] = __ldg(rays + 2 * (size_t)i + 1); db[k] = __ldg(rays + 2 * (size_t)i + 3);
+        }
         float sx = d1.x - d0.x, sy = d1.y - d0.y, sz = d1.z - d0.z;
         const bool by_origin = sx == 0.f && sy == 0.f && sz == 0.f;
         if (by_origin) { sx = o1.x - o0.x; sy = o1.y - o0.y; sz = o1.z - o0.z; }
@@ -596,9 +607,6 @@ __global__ void __launch_bounds__(1024) k_detect_grid(const float4* __restrict__
             const float4 a = __ldg(rays + 2 * (size_t)i + (by_origin ? 0 : 1)), b = __ldg(rays + 2 * (size_t)i + (by_origin ? 2 : 3));
             return (b.x - a.x) * sx + (b.y - a.y) * sy + (b.z - a.z) * sz < 0.f;
         };
-        if (threadIdx.x == 0) { s_first = s_second = 0xFFFFFFFFu; s_bad = 0; }
-        __syncthreads();
-        const uint32_t limit = min(count - 1, kGridSearch);
         bool     e[8];
         uint32_t w0 = 0;
         for (; usable && w0 < limit; w0 += 8 * 1024)
@@ -607,7 +615,8 @@ __global__ void __launch_bounds__(1024) k_detect_grid(const float4* __restrict__
             for (int k = 0; k < 8; ++k)
             {
                 const uint32_t i = w0 + k * 1024 + threadIdx.x;
-                e[k] = i < limit && row_end(i);
+                if (w0 == 0 && !by_origin) e[k] = i < limit && (db[k].x - da[k].x) * sx + (db[k].y - da[k].y) * sy + (db[k].z - da[k].z) * sz < 0.f;
+                else e[k] = i < limit && row_end(i);
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k)
@@ -665,7 +674,7 @@ __global__ void __launch_bounds__(1024) k_detect_grid(const float4* __restrict__
 // leaves (rr_internal.h node_update_word), and a leaf child is tested right where its box was -- its triangle is fetched only when
 // some ray's box test passed, and only the slots that have such a ray run the Moeller-Trumbore test (a leaf's box is small: 60 %
 // of the leaf visits of the C2 batch concern one of the two 32-ray slots only).  `cur` and the stack hold internal nodes only.
-template <bool kFullHit, int kOct>
+template <bool kFullHit, int kOct, bool kStatic>
 __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stack_lo, uint32_t gidx0, uint32_t gstep, const bool (&valid)[2],
                                              const float4 (&r0)[2], const float4 (&r1)[2], const RayState (&ray)[2])
 {
@@ -695,9 +704,10 @@ __device__ __forceinline__ bool trace_packet(const TraceParams& P, uint32_t stac
         {   // two internal children
             const bool     any0  = __any_sync(0xffffffffu, e0[0] <= e1[0] || e0[1] <= e1[1]);
             const bool     any1  = __any_sync(0xffffffffu, f0[0] <= f1[0] || f0[1] <= f1[1]);
-            // child 1 first when it is the nearer one for any slot-0 ray (a majority vote over the rays visits 0.3 % fewer nodes in the
-            // CPU model of the walk, and costs a POPC and two compares more per node)
-            const bool     first1 = __any_sync(0xffffffffu, f0[0] < e0[0]);
+            // child 1 first: the builder's static order for this octant on treelet-optimised trees (rr_internal.h node_order_bits:
+            // no FSETP, no VOTE), else when it is the nearer one for any slot-0 ray
+            // (which of the two: decided once per launch from the root's word, k_trace_packet -- a test per node costs more than either)
+            const bool first1 = kStatic ? (tag & (1u << (kNodeOrderShift + kOct))) != 0 : __any_sync(0xffffffffu, f0[0] < e0[0]);
             const bool     take1 = any1 && (!any0 || first1);
             if (any0 && any1)
             {   // defer the other child: one predicated store each instead of a select (the kernel is bound by the ALU pipe)
@@ -796,7 +806,9 @@ __global__ void __launch_bounds__(kPacketThreads, 8) k_trace_packet(TraceParams 
     // Packets need the builder's leaf flags and an internal root: a single-triangle geometry, or a node array that was not written
     // by this library's builder (no tag in the root's update word), goes to the per-ray kernel chunk by chunk.
     const uint32_t* root_words = reinterpret_cast<const uint32_t*>(P.bvh);
-    const bool packets_ok = __ldg(root_words + 3) != kInvalid && (__ldg(root_words + 15) & kNodeTagMask) == kNodeTag;
+    const uint32_t root_tag = __ldg(root_words + 15);
+    const bool packets_ok = __ldg(root_words + 3) != kInvalid && (root_tag & kNodeTagMask) == kNodeTag;
+    const bool static_order = (root_tag & kNodeVoteOrder) == 0;   // a treelet-optimised tree (rr_internal.h)
     const RayGrid  G = load_grid(P.grid, count);
     const uint64_t packets = G.w ? (uint64_t)G.tiles_x * G.tiles_y : ((uint64_t)count + 63) / 64;
     while (true)
@@ -832,16 +844,33 @@ __global__ void __launch_bounds__(kPacketThreads, 8) k_trace_packet(TraceParams 
         bool done = false;
         if (coherent)
         {
-            switch (oct0)
+            if (static_order)
             {
-            case 0: done = trace_packet<kFullHit, 0>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
-            case 1: done = trace_packet<kFullHit, 1>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
-            case 2: done = trace_packet<kFullHit, 2>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
-            case 3: done = trace_packet<kFullHit, 3>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
-            case 4: done = trace_packet<kFullHit, 4>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
-            case 5: done = trace_packet<kFullHit, 5>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
-            case 6: done = trace_packet<kFullHit, 6>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
-            default: done = trace_packet<kFullHit, 7>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                switch (oct0)
+                {
+                case 0: done = trace_packet<kFullHit, 0, true>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 1: done = trace_packet<kFullHit, 1, true>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 2: done = trace_packet<kFullHit, 2, true>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 3: done = trace_packet<kFullHit, 3, true>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 4: done = trace_packet<kFullHit, 4, true>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 5: done = trace_packet<kFullHit, 5, true>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 6: done = trace_packet<kFullHit, 6, true>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                default: done = trace_packet<kFullHit, 7, true>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                }
+            }
+            else
+            {
+                switch (oct0)
+                {
+                case 0: done = trace_packet<kFullHit, 0, false>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 1: done = trace_packet<kFullHit, 1, false>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 2: done = trace_packet<kFullHit, 2, false>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 3: done = trace_packet<kFullHit, 3, false>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 4: done = trace_packet<kFullHit, 4, false>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 5: done = trace_packet<kFullHit, 5, false>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                case 6: done = trace_packet<kFullHit, 6, false>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                default: done = trace_packet<kFullHit, 7, false>(P, stack, gidx[0], gstep, valid, r0, r1, ray); break;
+                }
             }
         }
         if (!done && lane == 0)

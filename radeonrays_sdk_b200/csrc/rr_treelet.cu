@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kTreeletWarps * 32)
                 np[0] = pack(llo, c0);
                 np[1] = pack(lhi, c1);
                 np[2] = pack(rlo, S.in_parent[slot]);
-                np[3] = pack(rhi, node_update_word(c0, c1, n - 1u, internal_update[slot]));  // leaf flags follow the new children
+                np[3] = pack(rhi, node_update_word(c0, c1, n - 1u, internal_update[slot], node_order_bits(llo, lhi, rlo, rhi)));  // flags follow the new children
             }
             if (lane < 7) reinterpret_cast<uint32_t*>(nodes + my_leaf)[11] = S.leaf_parent[lane];
         }

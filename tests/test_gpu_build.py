@@ -110,6 +110,16 @@ def test_sponza_fast_build(engine, sponza):
     _check_build(engine, pos, idx)
 
 
+def test_update_words_after_builds(engine, sponza, cornell):
+    """Leaf flags / child order / tag in the update word after a fast build, a quality build and a Karras-tree refit."""
+    for (pos, idx, _), flags in ((sponza, api.RR_BUILD_FLAG_BITS_PREFER_FAST_BUILD), (sponza, 0), (cornell, 0)):
+        g = engine.build_geometry(pos, idx, build_flags=flags)
+        vote = flags != 0 or idx.shape[0] < 64          # (the treelet pass leaves trees below its 64-primitive floor alone)
+        _check_update_words(g.nodes(), idx.shape[0], vote=vote)
+        engine.update_geometry(g, (pos * np.float32(2.0)).astype(np.float32))
+        _check_update_words(g.nodes(), idx.shape[0], vote=vote)
+
+
 def test_sponza_quality_build_matches_oracle_treelets(engine, sponza):
     pos, idx, _ = sponza
     g, nodes = _check_build(engine, pos, idx, flags=0)
@@ -194,6 +204,37 @@ def test_update_after_quality_build(engine, sponza):
     moved = (pos * np.float32(1.5)).astype(np.float32)
     engine.update_geometry(g, moved)
     assert_nodes_equal(g.nodes(), O.refit(before, moved, idx))
+    _check_update_words(g.nodes(), idx.shape[0])
+    # ... and twice more (the rendezvous parity toggles; the builder's flags in the same word must survive), then traced by the
+    # packet kernel, which relies on those flags
+    for scale in (0.5, 1.25):
+        moved = (pos * np.float32(scale)).astype(np.float32)
+        engine.update_geometry(g, moved)
+    nodes = g.nodes()
+    assert_nodes_equal(nodes, O.refit(before, moved, idx))
+    _check_update_words(nodes, idx.shape[0])
+    rays = W.sponza_primary_rays(320, 200)
+    rays["origin"] *= np.float32(1.25)
+    assert_hits_equal(engine.intersect(g, rays), O.trace(nodes, rays), what="after refit", mesh=(moved, idx), rays=rays)
+
+
+def _check_update_words(nodes, n, vote=False):
+    """The builder's side of VkBvhNode::update (rr_internal.h node_update_word): tag, leaf flags that match the children, an even
+    rendezvous parity after a complete refit, and a child order that is a function of one axis (a table of the form M or ~M)."""
+    u = nodes["update"][: n - 1]
+    assert np.all(u >> 16 == 0x52A5), "tag"
+    assert np.all(u & 1 == 0), "rendezvous parity must be even between refits"
+    assert np.all((u >> 3) & 1 == int(vote)), "vote-order flag: set by fast builds (plain LBVH), clear on treelet-optimised trees"
+    assert np.array_equal((u >> 1) & 1, (nodes["child0"][: n - 1] >= n - 1).astype(np.uint32)), "child0-is-leaf flag"
+    assert np.array_equal((u >> 2) & 1, (nodes["child1"][: n - 1] >= n - 1).astype(np.uint32)), "child1-is-leaf flag"
+    order = (u >> 8) & 0xFF
+    assert np.all(np.isin(order, [0xAA, 0x55, 0xCC, 0x33, 0xF0, 0x0F])), "child order table"
+    # the order follows the boxes: child1 first for the octants that look from its side
+    c = (nodes["aabb1_min_or_v2"][: n - 1] + nodes["aabb1_max_or_v3"][: n - 1]) - (nodes["aabb0_min_or_v0"][: n - 1] + nodes["aabb0_max_or_v1"][: n - 1])
+    axis = np.where((np.abs(c[:, 0]) >= np.abs(c[:, 1])) & (np.abs(c[:, 0]) >= np.abs(c[:, 2])), 0, np.where(np.abs(c[:, 1]) >= np.abs(c[:, 2]), 1, 2))
+    neg = np.array([0xAA, 0xCC, 0xF0], np.uint32)[axis]
+    want = np.where(c[np.arange(n - 1), axis] < 0, ~neg & 0xFF, neg)
+    assert np.array_equal(order, want), "child order does not follow the boxes"
 
 
 def test_update_after_debug_restructure(engine, sponza):
