@@ -299,8 +299,12 @@ def run_ours(args):
         ctx.set_option(api.RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, 1)      # the reference's tie rule: per-ray kernel (k_trace), no packets
         ms_ff = timed(resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, CLOSEST, rb.p_rays, n_rays, None, FULL, rb.p_hits, rb.p_scratch, s)), args.steps, 1) / args.steps
         ctx.set_option(api.RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, 0)
+        ctx.set_option(api.RR_CUDA_OPTION_RAY_GRID_WIDTH, 1)                    # packets of 64 consecutive rays instead of 8 x 8 tiles of the image
+        ms_strips = timed(resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, CLOSEST, rb.p_rays, n_rays, None, FULL, rb.p_hits, rb.p_scratch, s)), args.steps, 1) / args.steps
+        ctx.set_option(api.RR_CUDA_OPTION_RAY_GRID_WIDTH, 0)
         variants = {"closest_full_hit_other_bvh_mrays": round(n_rays / ms_other / 1e3, 1), "any_hit_ids_mrays": round(n_rays / ms_any / 1e3, 1),
-                    "closest_first_found_rule_per_ray_kernel_mrays": round(n_rays / ms_ff / 1e3, 1)}
+                    "closest_first_found_rule_per_ray_kernel_mrays": round(n_rays / ms_ff / 1e3, 1),
+                    "closest_full_hit_64x1_strip_packets_mrays": round(n_rays / ms_strips / 1e3, 1)}
 
     # ---- trace: end to end through the C ABI with host buffers ------------------------------------------------
     from radeonrays_sdk_b200.host import HostTracePipeline
@@ -354,7 +358,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": ncu["dram_bytes"] if same_kernel_config else None,
-                     "peak_source": peak_src, "kernel": "k_trace_packet<full_hit> (+ k_trace for declined chunks)",
+                     "peak_source": peak_src, "kernel": "k_trace_packet<full_hit> (8 x 8 ray tiles found by k_detect_grid; + k_trace for declined chunks)",
                      "algorithmic_bytes_per_launch": BYTES_PER_RAY * n_rays,
                      "note": "48 B/ray compulsory (32 B ray + 16 B hit), BVH L2-resident: HBM is not the bound; the kernel is bound by the SM's "
                              "ALU pipe / issue slots (profiles/round2_summary.md)",

@@ -417,7 +417,7 @@ __device__ __forceinline__ MergeOut group_merge(StoreNode&& store_node, int n, i
         lane_range_reduce<false>(hi.z, lane, lenL, pr, lenR, hiL.z, hiR.z);
     }
     if (formed)
-        store_node(idx, pack(loL, c0), pack(hiL, c1), pack(loR, parent_in ? pidx : kInvalid), pack(hiR, node_update_word(c0, c1, (uint32_t)n - 1u, 0u, node_order_bits(loL, hiL, loR, hiR) | order_flag)));
+        store_node(idx, pack(loL, c0), pack(hiL, c1), pack(loR, parent_in ? pidx : kInvalid), pack(hiR, node_update_word(c0, c1, (uint32_t)n - 1u, 0u, order_flag ? order_flag : node_order_bits(loL, hiL, loR, hiR))));  // (no table where the traversal votes)
 
     // the elements themselves: parent = the node split at the larger of the two neighbouring deltas
     int Dprev = __shfl_up_sync(full, D, 1);
@@ -944,8 +944,8 @@ __device__ __forceinline__ void refit_climb_in_place(Node* __restrict__ nodes, i
         float3 slo, shi;
         node_box(s0, s1, s2, s3, sib >= (uint32_t)leaf0, slo, shi);
         // (the update word: parity as the atomicXor left it, leaf flags as they were, child order for the new boxes)
-        if (is_left) { pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up); pp[3] = pack(shi, node_update_word(c0, c1, (uint32_t)leaf0, old ^ 1u, node_order_bits(lo, hi, slo, shi) | (old & kNodeVoteOrder))); }
-        else { pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up); pp[3] = pack(hi, node_update_word(c0, c1, (uint32_t)leaf0, old ^ 1u, node_order_bits(slo, shi, lo, hi) | (old & kNodeVoteOrder))); }
+        if (is_left) { pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up); pp[3] = pack(shi, node_update_word(c0, c1, (uint32_t)leaf0, old ^ 1u, ((old & kNodeVoteOrder) ? kNodeVoteOrder : node_order_bits(lo, hi, slo, shi)))); }
+        else { pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up); pp[3] = pack(hi, node_update_word(c0, c1, (uint32_t)leaf0, old ^ 1u, ((old & kNodeVoteOrder) ? kNodeVoteOrder : node_order_bits(slo, shi, lo, hi)))); }
         lo = min3(lo, slo);
         hi = max3(hi, shi);
         me = parent;
@@ -1033,12 +1033,12 @@ __global__ void __launch_bounds__(256)
                 if (is_left)
                 {
                     pp[0] = pack(lo, c0); pp[1] = pack(hi, c1); pp[2] = pack(slo, up);
-                    pp[3] = pack(shi, node_update_word(c0, c1, leaf0, old ^ 1u, node_order_bits(lo, hi, slo, shi) | (old & kNodeVoteOrder)));
+                    pp[3] = pack(shi, node_update_word(c0, c1, leaf0, old ^ 1u, ((old & kNodeVoteOrder) ? kNodeVoteOrder : node_order_bits(lo, hi, slo, shi))));
                 }
                 else
                 {
                     pp[0] = pack(slo, c0); pp[1] = pack(shi, c1); pp[2] = pack(lo, up);
-                    pp[3] = pack(hi, node_update_word(c0, c1, leaf0, old ^ 1u, node_order_bits(slo, shi, lo, hi) | (old & kNodeVoteOrder)));
+                    pp[3] = pack(hi, node_update_word(c0, c1, leaf0, old ^ 1u, ((old & kNodeVoteOrder) ? kNodeVoteOrder : node_order_bits(slo, shi, lo, hi))));
                 }
                 lo = min3(lo, slo);
                 hi = max3(hi, shi);
@@ -1198,7 +1198,7 @@ __global__ void __launch_bounds__(256, 4)  // 64 registers; 3 / 5 / 6 CTAs per S
                     const uint32_t c0 = wbits(h0), c1 = wbits(h1), up = wbits(h2), upd = wbits(h3);
                     const bool     first = c0 == cur;  // which of the two is child0
                     st_node(nodes + par, pack(first ? lo : nlo, c0), pack(first ? hi : nhi, c1), pack(first ? nlo : lo, up),
-                            pack(first ? nhi : hi, (upd & ~(0xFFu << kNodeOrderShift)) |
+                            pack(first ? nhi : hi, (upd & kNodeVoteOrder) ? upd : (upd & ~(0xFFu << kNodeOrderShift)) |
                                                        (first ? node_order_bits(lo, hi, nlo, nhi) : node_order_bits(nlo, nhi, lo, hi))));
                     lo = min3(lo, nlo);
                     hi = max3(hi, nhi);
@@ -1300,7 +1300,7 @@ __global__ void __launch_bounds__(256)
                     const uint32_t  c0 = __ldcg(pw + 3), c1 = __ldcg(pw + 7), up = __ldcg(pw + 11), upd = __ldcg(pw + 15);
                     const bool      first = c0 == id;  // which of the two is child0
                     st_node(nodes + par, pack(first ? lo : nlo, c0), pack(first ? hi : nhi, c1), pack(first ? nlo : lo, up),
-                            pack(first ? nhi : hi, (upd & ~(0xFFu << kNodeOrderShift)) |
+                            pack(first ? nhi : hi, (upd & kNodeVoteOrder) ? upd : (upd & ~(0xFFu << kNodeOrderShift)) |
                                                        (first ? node_order_bits(lo, hi, nlo, nhi) : node_order_bits(nlo, nhi, lo, hi))));
                     lo = min3(lo, nlo);
                     hi = max3(hi, nhi);

@@ -228,6 +228,9 @@ def _check_update_words(nodes, n, vote=False):
     assert np.array_equal((u >> 1) & 1, (nodes["child0"][: n - 1] >= n - 1).astype(np.uint32)), "child0-is-leaf flag"
     assert np.array_equal((u >> 2) & 1, (nodes["child1"][: n - 1] >= n - 1).astype(np.uint32)), "child1-is-leaf flag"
     order = (u >> 8) & 0xFF
+    if vote:
+        assert np.all(order == 0), "no order table where the traversal votes"
+        return
     assert np.all(np.isin(order, [0xAA, 0x55, 0xCC, 0x33, 0xF0, 0x0F])), "child order table"
     # the order follows the boxes: child1 first for the octants that look from its side
     c = (nodes["aabb1_min_or_v2"][: n - 1] + nodes["aabb1_max_or_v3"][: n - 1]) - (nodes["aabb0_min_or_v0"][: n - 1] + nodes["aabb0_max_or_v1"][: n - 1])
