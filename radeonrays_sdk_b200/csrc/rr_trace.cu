@@ -223,8 +223,8 @@ struct TraceParams
     uint32_t*             packet_ticket;  // word 3: packet counter of k_trace_packet
     uint32_t*             chunk_count;    // word 4: 32-ray chunks k_trace_packet handed to the per-ray kernel
     uint32_t*             chunk_list;     // [ceil(ray_count / 32)] their chunk indices; nullptr: k_trace walks all chunks itself
-    const uint32_t*       grid;           // words 5, 6: row length of the ray grid k_detect_grid found (0: none) and the (signed) ray index
-                                          // of the first ray of its row 0; nullptr: packets / chunks of consecutive rays
+    const uint32_t*       grid;           // words 5, 6, 7: row length of the ray grid k_detect_grid found (0: none) and the (signed) ray index
+                                          // of the first ray of its row 0; "the batch is incoherent"; nullptr: packets / chunks of consecutive rays
     const uint32_t*       perm;           // RR_CUDA_OPTION_SORT_RAYS: position -> ray index in binned order; nullptr: client order
     int                   first_found;
     int                   force_generic;
@@ -252,6 +252,7 @@ __device__ __forceinline__ bool resolve_scene(TraceParams& P)
 
 // Ray grids (k_detect_grid below): the mapping from (tile, half, lane) to a ray index, shared by k_trace_packet and k_trace.
 constexpr uint32_t kGridMinWidth = 64, kGridMinRows = 8, kGridSearch = 32768;
+constexpr uint32_t kAllChunks = 0xFFFFFFFFu;   // chunk count that means "no list: every 32-ray chunk of the batch"
 struct RayGrid
 {
     uint32_t w;         // 0: no grid
@@ -429,8 +430,10 @@ __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(Tra
     const uint32_t lane = threadIdx.x & 31;
     SmemStack<kEntries> st;
     st.base = s_stack + threadIdx.x;
-    const RayGrid G = load_grid(kList ? P.grid : nullptr, count);
-    if (kList && *P.chunk_count == 0) return;   // (coherent batches: nothing was declined; no ticket traffic for nothing)
+    const uint32_t listed = kList ? *P.chunk_count : 0u;
+    if (kList && listed == 0) return;   // (coherent batches: nothing was declined; no ticket traffic for nothing)
+    const bool    all = kList && listed == kAllChunks;   // k_trace_packet stood aside: every chunk, in order
+    const RayGrid G = load_grid(kList && !all ? P.grid : nullptr, count);
     while (true)
     {
         uint32_t chunk = 0;
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTwoLevel ? 8 : 10) k_trace(Tra
         {
             chunk = atomicAdd(P.ticket, 1u);
             // list mode: only the chunks the packet kernel declined (incoherent rays, deep trees)
-            if (kList) chunk = chunk < *P.chunk_count ? P.chunk_list[chunk] : kInvalid;
+            if (kList && !all) chunk = chunk < listed ? P.chunk_list[chunk] : kInvalid;
         }
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         uint32_t gidx;
@@ -584,7 +587,31 @@ __global__ void __launch_bounds__(1024) k_detect_grid(const float4* __restrict__
     if (indirect) count = min(count, __ldg(indirect));
     uint32_t w = 0;
     int32_t  base = 0;
-    if (explicit_w >= kGridMinWidth) w = explicit_w;
+    // An incoherent batch (diffuse bounces) would only be read once more by the packet kernel to be declined 64 rays at a time:
+    // 4 096 pairs of consecutive rays spread over the batch say so beforehand (word 2: the packet kernel hands ALL chunks to the
+    // per-ray kernel at once).  Camera rays change octant on a few lines of the image; a quarter of the pairs is far from that.
+    uint32_t mixed = 0;
+    if (explicit_w == 0 && count >= 8192)
+    {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const uint32_t i = (uint32_t)(((uint64_t)(threadIdx.x * 4 + k) * (count - 1)) >> 12);
+            a[k] = __ldg(rays + 2 * (size_t)i + 1); b[k] = __ldg(rays + 2 * (size_t)i + 3);
+        }
+        int differ = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            differ += ((__float_as_uint(a[k].x) ^ __float_as_uint(b[k].x)) | (__float_as_uint(a[k].y) ^ __float_as_uint(b[k].y)) |
+                       (__float_as_uint(a[k].z) ^ __float_as_uint(b[k].z))) >> 31;
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) total += __syncthreads_count(differ > k);   // sum over the block of `differ` (0..4)
+        mixed = total > 1024 ? 1u : 0u;
+    }
+    if (mixed) { /* nothing to tile */ }
+    else if (explicit_w >= kGridMinWidth) w = explicit_w;
     else if (count >= kGridMinWidth * kGridMinRows)
     {
         // the step along a row: directions, or origins when the first two directions are equal (parallel rays)
@@ -662,6 +689,7 @@ __global__ void __launch_bounds__(1024) k_detect_grid(const float4* __restrict__
         }
         words[0] = w;
         words[1] = (uint32_t)base;
+        words[2] = mixed;
     }
 }
 
@@ -809,6 +837,11 @@ __global__ void __launch_bounds__(kPacketThreads, 8) k_trace_packet(TraceParams 
     const uint32_t root_tag = __ldg(root_words + 15);
     const bool packets_ok = __ldg(root_words + 3) != kInvalid && (root_tag & kNodeTagMask) == kNodeTag;
     const bool static_order = (root_tag & kNodeVoteOrder) == 0;   // a treelet-optimised tree (rr_internal.h)
+    if (P.grid && __ldg(P.grid + 2))
+    {   // k_detect_grid found the batch incoherent: every chunk goes to the per-ray kernel, which then runs as if there were no list
+        if (blockIdx.x == 0 && threadIdx.x == 0) *P.chunk_count = kAllChunks;
+        return;
+    }
     const RayGrid  G = load_grid(P.grid, count);
     const uint64_t packets = G.w ? (uint64_t)G.tiles_x * G.tiles_y : ((uint64_t)count + 63) / 64;
     while (true)

@@ -250,10 +250,11 @@ def test_ray_binning_option_is_bit_identical(engine, sponza, cornell):
     assert_hits_equal(got, O.trace(g.nodes(), diffuse), what="binned diffuse", mesh=(pos, idx), rays=diffuse)
 
 
-def _grid_words(engine):
-    """Scratch header words 5 / 6 after an rrCmdIntersect: the row length k_detect_grid settled on (0: none) and the phase of row 0."""
-    w = engine.last_ray_buffers.d_scratch[20:28].cpu().numpy().view(np.int32)
-    return int(w[0]), int(w[1])
+def _grid_words(engine, with_mixed=False):
+    """Scratch header words 5 / 6 (/ 7) after an rrCmdIntersect: the row length k_detect_grid settled on (0: none), the phase of
+    row 0 (and whether it found the batch incoherent, so that the packet kernel stood aside)."""
+    w = engine.last_ray_buffers.d_scratch[20:32].cpu().numpy().view(np.int32)
+    return (int(w[0]), int(w[1]), int(w[2])) if with_mixed else (int(w[0]), int(w[1]))
 
 
 def test_ray_grid_tiles_are_bit_identical(engine, sponza):
@@ -296,6 +297,15 @@ def test_ray_grid_tiles_are_bit_identical(engine, sponza):
     assert ctx.lib.rrCudaSetOption(ctx.handle, api.RR_CUDA_OPTION_RAY_GRID_WIDTH, 17) == api.RR_ERROR_INVALID_PARAMETER
     # tiles against the oracle (the parity tests above run with detection on as well: it is the default)
     assert_hits_equal(run(img, 0)[0], O.trace(g.nodes(), img), what="tiles", mesh=(pos, idx), rays=img)
+    # incoherent batches are recognised beforehand (the packet kernel stands aside), camera rays are not mistaken for one
+    assert _grid_words(engine, True)[2] == 0
+    prim = W.sponza_primary_rays(256, 256)
+    diffuse = W.diffuse_rays(pos, idx, prim, engine.intersect(g, prim), count=100_003)
+    a, _ = run(diffuse, 1)
+    b, _ = run(diffuse, 0)
+    assert _grid_words(engine, True) == (0, 0, 1), "the diffuse batch should be found incoherent"
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    assert_hits_equal(b, O.trace(g.nodes(), diffuse), what="incoherent shortcut", mesh=(pos, idx), rays=diffuse)
     # jittered camera rays: consecutive steps may turn back anywhere, nothing to tile, same hits
     jit = img.copy()
     jit["direction"] += rng.normal(0, 2e-3, jit["direction"].shape).astype(np.float32)
