@@ -288,7 +288,11 @@ def run_ours(args):
                  "rank0_buffer_equals_local_trace_of_every_frame": ok, "nvlink_bytes_per_step": (world - 1) * 16 * n_rays,
                  "nvlink_gbs_into_rank0": round((world - 1) * 16 * n_rays / (ms_step * 1e-3) / 1e9, 1),
                  "local_trace_only_ms": round(ms_local, 4), "nccl_gather_only_ms": round(ms_gather, 4),
-                 "trace_then_nccl_gather_ms": round(ms_nccl, 4), "fused_ms": round(ms_step, 4)}
+                 "trace_then_nccl_gather_ms": round(ms_nccl, 4), "fused_ms": round(ms_step, 4),
+                 # one GPU can take in (world - 1) frames of 16-byte hits no faster than its NVLink ports deliver them
+                 "mrays_per_s_if_hits_stayed_local": round(n_rays * world / ms_local / 1e3, 1),
+                 "limiter": ("NVLink into rank 0: %d MB of hits per step, %.0f GB/s" % ((world - 1) * 16 * n_rays // 1000000, (world - 1) * 16 * n_rays / (ms_step * 1e-3) / 1e9)
+                             if ms_step > 1.05 * ms_local else "the trace itself (the gather hides behind it)")}
 
     # the other trace flavours of the metric (any-hit; the other BVH; the per-ray kernel), device resident, same batch (N=1 only)
     variants = None
