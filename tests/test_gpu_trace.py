@@ -257,6 +257,24 @@ def _grid_words(engine, with_mixed=False):
     return (int(w[0]), int(w[1]), int(w[2])) if with_mixed else (int(w[0]), int(w[1]))
 
 
+def _normalised(rays):
+    out = rays.copy()
+    d = out["direction"].astype(np.float64)
+    out["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    return out
+
+
+def _orthographic(w, h):
+    """Parallel rays through Sponza's nave from a w x h grid of origins: all directions equal, the ORIGINS step along a row."""
+    rays = np.zeros(w * h, W.RAY_DTYPE)
+    x = np.arange(w, dtype=np.float32)[None, :].repeat(h, 0)
+    y = np.arange(h, dtype=np.float32)[:, None].repeat(w, 1)
+    rays["origin"] = np.stack([np.full((h, w), 12.0, np.float32), 1.0 + 12.0 * y / h, -4.0 + 8.0 * x / w], -1).reshape(-1, 3)
+    rays["direction"] = (-1.0, 0.02, 0.01)
+    rays["min_t"], rays["max_t"] = 0.001, 1e5
+    return rays
+
+
 def test_ray_grid_tiles_are_bit_identical(engine, sponza):
     """Closest-hit packets are 8 x 8 tiles of the ray grid when the batch is an image in row order (k_detect_grid finds the row
     length on the device; RR_CUDA_OPTION_RAY_GRID_WIDTH).  The grouping must never change a hit: tiles (detected, and told), and
@@ -282,7 +300,10 @@ def test_ray_grid_tiles_are_bit_identical(engine, sponza):
              ("wide and short", W.sponza_primary_rays(1024, 9), 1024, 0, {}),
              ("seven rows: strips", W.sponza_primary_rays(1024, 7), 0, 0, {}),
              ("63 columns: strips", W.sponza_primary_rays(63, 200), 0, 0, {}),
-             ("shuffled rows: strips", img[rng.permutation(img.shape[0])], 0, 0, {})]
+             ("shuffled rows: strips", img[rng.permutation(img.shape[0])], 0, 0, {}),
+             ("normalised directions", _normalised(img), 331, 0, {}),
+             ("orthographic camera", _orthographic(200, 120), 200, 0, {}),
+             ("8K rows: second search round", W.sponza_primary_rays(7680, 9), 7680, 0, {})]
     for what, rays, want_w, want_base, kw in cases:
         strips, (w1, _) = run(rays, 1, **kw)
         tiles, (w0, b0) = run(rays, 0, **kw)
