@@ -309,6 +309,10 @@ def test_ray_grid_tiles_are_bit_identical(engine, sponza):
         tiles, (w0, b0) = run(rays, 0, **kw)
         assert w1 == 0 and (w0, b0) == (want_w, want_base), f"{what}: k_detect_grid said W = {w0}, row 0 starts at ray {b0}"
         assert np.array_equal(strips.view(np.uint8), tiles.view(np.uint8)), f"{what}: tiles and strips differ"
+        # the per-ray kernel takes its 32-ray chunks as 8 x 4 half tiles of the same grid: any-hit ids, bit for bit
+        a, _ = run(rays, 1, query=ANY, output=IDS, **kw)
+        b, (w0, _) = run(rays, 0, query=ANY, output=IDS, **kw)
+        assert w0 == want_w and np.array_equal(a, b), f"{what}: any-hit ids differ between 8 x 4 tiles and 32-ray chunks"
     # the client may state the row length (then row 0 starts at ray 0); a wrong one only costs coherence
     strips, _ = run(img, 1)
     for w in (331, 300, 4096):
