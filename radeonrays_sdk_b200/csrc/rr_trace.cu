@@ -8,7 +8,8 @@
 //    reference's, which is what makes ANY-hit ids and first-found closest hits reproducible: it serves ANY queries, everything
 //    two-level, RR_CUDA_OPTION_CLOSEST_HIT_KEEP_FIRST_FOUND, and whatever the packet kernel declines.
 //  * k_trace_packet -- closest hits under the default (t, prim) rule for coherent rays: 64 rays per warp share ONE walk
-//    (see the comment above it).  6.05 -> 7.24 Grays/s on the C2 batch.
+//    (see the comment above it); the 64 rays are an 8 x 8 tile of the image when k_detect_grid finds the batch to be one in
+//    row order.  6.05 -> 9.4 Grays/s on the C2 batch.
 //
 // B200 mapping of k_trace:
 //  * persistent CTAs (a multiple of the SM count); each warp pulls 32-ray chunks from a ticket, so per-thread state
