@@ -339,6 +339,36 @@ def test_ray_grid_tiles_are_bit_identical(engine, sponza):
     assert w0 == 0 and np.array_equal(a.view(np.uint8), b.view(np.uint8))
 
 
+def test_node_array_without_builder_tags(engine, sponza):
+    """A VkBvhNode array that this builder did not write (a dump of the reference's, uploaded by the client) has small refit
+    counters in its `update` words, not the builder's tag / leaf flags / child order (rr_internal.h node_update_word): the packet
+    kernel must stand aside and the per-ray kernel must return the oracle's walk bit for bit, in tiles and in strips."""
+    import torch
+    pos, idx, _ = sponza
+    g = engine.build_geometry(pos, idx, build_flags=0)
+    n_nodes = 2 * idx.shape[0] - 1
+    words = g.d_nodes[: 64 * n_nodes].view(torch.int32).view(n_nodes, 16)
+    saved = words[:, 15].clone()
+    rays = W.sponza_primary_rays(320, 200)
+    want = O.trace(g.nodes(), rays)
+    try:
+        for filler in (0, 2):                                  # what the reference leaves there: 0 after a build, 2 after an update
+            words[:, 15] = filler
+            for mode in (0, 1):
+                engine.ctx.set_option(api.RR_CUDA_OPTION_RAY_GRID_WIDTH, mode)
+                assert_hits_equal(engine.intersect(g, rays), want, what=f"untagged nodes, update = {filler}, grid mode {mode}")
+            assert np.array_equal(engine.intersect(g, rays, ANY, IDS), O.trace(g.nodes(), rays, O.QUERY_ANY, O.OUTPUT_INSTANCE_ID))
+    finally:
+        engine.ctx.set_option(api.RR_CUDA_OPTION_RAY_GRID_WIDTH, 0)
+        words[:, 15] = saved
+    # ... and a refit of such an array puts the builder's words back (the generic refit rewrites every parent it fits)
+    words[: idx.shape[0] - 1, 15] = 0
+    engine.update_geometry(g, pos)
+    u = g.nodes()["update"][: idx.shape[0] - 1]
+    assert np.all(u >> 16 == 0x52A5) and np.all(u & 1 == 0)
+    assert_hits_equal(engine.intersect(g, rays), want, what="after refit", mesh=(pos, idx), rays=rays)
+
+
 def test_degenerate_rays_and_triangles(engine, cornell):
     """Edge cases the arithmetic must survive exactly like the oracle: rays with zero / denormal / huge direction components
     (safe_invdir, common.h:166-183), axis-parallel rays, origins on a vertex / edge / face, max_t below min_t, infinite max_t,
