@@ -244,7 +244,7 @@ def run_ours(args):
     h_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).pin_memory()
     h_hits = torch.empty(16 * n_rays, dtype=torch.uint8).pin_memory()
     rb.d_rays[: 32 * n_rays].copy_(h_rays)
-    peer = None
+    peer, ring = None, []
     p_hits = rb.p_hits
     if world > 1:
         peer = sharding.PeerHitBuffer(ctx, world * 16 * n_rays, root=0)
@@ -281,6 +281,15 @@ def run_ours(args):
 
         def nccl_only():
             dist.gather(src, dst, dst=0)
+        # (c) the same fused stores with a DISTRIBUTED destination: the hits of frame r are delivered to rank (r + 1) mod N, so every
+        # hit still crosses NVLink inside the timed region but every GPU takes in one frame instead of rank 0 taking in N - 1
+        ring = [sharding.PeerHitBuffer(ctx, 16 * n_rays, root=r) for r in range(world)]
+        p_next = ring[(rank + 1) % world].ptr(0)
+        ring_trace = resubmitter(lambda s: ctx.cmd_intersect(geom.p_nodes, CLOSEST, rb.p_rays, n_rays, None, FULL, p_next, rb.p_scratch, s))
+        ms_ring = timed(ring_trace, max(5, args.steps // 2), 3) / max(5, args.steps // 2)
+        mine = ring[rank].read(W.HIT_DTYPE)                                 # what the previous rank delivered: its frame
+        ring_ok = torch.tensor([int(np.array_equal(mine.view(np.uint8), eng.intersect(geom, frame_rays((rank - 1) % world)).view(np.uint8)))], device=dev)
+        dist.all_reduce(ring_ok, op=dist.ReduceOp.MIN)
         ms_nccl = timed(nccl_step, max(3, args.steps // 4), 2) / max(3, args.steps // 4)
         ms_gather = timed(nccl_only, max(3, args.steps // 4), 2) / max(3, args.steps // 4)
         ms_local = timed(local_trace, max(3, args.steps // 4), 2) / max(3, args.steps // 4)
@@ -291,6 +300,10 @@ def run_ours(args):
                  "trace_then_nccl_gather_ms": round(ms_nccl, 4), "fused_ms": round(ms_step, 4),
                  # one GPU can take in (world - 1) frames of 16-byte hits no faster than its NVLink ports deliver them
                  "mrays_per_s_if_hits_stayed_local": round(n_rays * world / ms_local / 1e3, 1),
+                 "delivered_to_next_rank": {"what": "hits of frame r stored into rank (r + 1) mod N's buffer by the traversal kernels: every hit crosses NVLink, every GPU takes in one frame",
+                                            "ms": round(ms_ring, 4), "mrays_per_s": round(n_rays * world / ms_ring / 1e3, 1),
+                                            "nvlink_gbs_into_each_rank": round(16 * n_rays / (ms_ring * 1e-3) / 1e9, 1),
+                                            "every_rank_holds_the_previous_ranks_frame": bool(ring_ok.item())},
                  "limiter": ("NVLink into rank 0: %d MB of hits per step, %.0f GB/s" % ((world - 1) * 16 * n_rays // 1000000, (world - 1) * 16 * n_rays / (ms_step * 1e-3) / 1e9)
                              if ms_step > 1.05 * ms_local else "the trace itself (the gather hides behind it)")}
 
@@ -385,6 +398,8 @@ def run_ours(args):
     if peer is not None:
         barrier()
         peer.close()
+        for b in ring:
+            b.close()
     for cs in streams:
         ctx.release_command_stream(cs)
     eng.close()
